@@ -1,0 +1,130 @@
+/* libvdd -- C ABI of the B200-native Visual-Debias-Decoding (VDD) hot path.
+ *
+ * The reference (yfzhang114/LLaVA-Align) is pure Python and has no FFI of its own; its boundary for this path is
+ *   - evolve_vcd_sampling()                              reference vcd_utils/vcd_sample.py:325-326
+ *   - model.generate(input_ids, images=, use_dd=, ...)   reference experiments/eval/sampling/llava_sampling.py:96-109
+ * The Python package llava_align_b200 keeps that surface and binds the entry points below with ctypes
+ * (llava_align_b200/_lib.py).  INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions: every call returns 0 on success and a negative code on failure (text via vdd_last_error());
+ * pointers are DEVICE pointers unless the name ends in _host; all work is enqueued on the caller's stream
+ * (a cudaStream_t passed as void*), no hidden synchronisation unless stated; one engine is used from one
+ * host thread; tensor-parallel runs use one engine per rank.  No torch types appear here.
+ */
+#ifndef VDD_H_
+#define VDD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VDD_API __attribute__((visibility("default")))
+#else
+#define VDD_API
+#endif
+
+#define VDD_OK 0
+#define VDD_ERR_ARG (-1)
+#define VDD_ERR_CUDA (-2)
+#define VDD_ERR_STATE (-3)
+#define VDD_ERR_UNSUPPORTED (-4)
+
+#define VDD_IMAGE_TOKEN_INDEX (-200) /* reference experiments/llava/constants.py:9 */
+
+typedef struct vdd_engine vdd_engine;
+
+/* Model dimensions: the HF config.json values of the checkpoints the reference loads
+ * (reference experiments/llava/model/builder.py:97-103, multimodal_encoder/clip_encoder.py:22-27). */
+typedef struct vdd_config {
+  int32_t hidden_size, intermediate_size, num_layers, num_heads, vocab_size, max_position;
+  float rms_eps, rope_theta;
+  int32_t v_hidden, v_intermediate, v_layers, v_layers_used, v_heads, image_size, patch_size;
+  float v_ln_eps;
+  int32_t tp_size, tp_rank; /* tensor parallel: heads / FFN columns / vocab are split tp_size ways */
+} vdd_config;
+
+/* Sampler parameters = the generate() kwargs the patched sampler reads (reference vcd_sample.py:122-124,
+ * 188-189) plus the HF warper settings (temperature/top_k/top_p). */
+typedef struct vdd_sample_params {
+  float cd_alpha;     /* reference default 0.5 (vcd_sample.py:188) */
+  float log_cd_beta;  /* log(cd_beta) evaluated by the host in fp32, as torch.log(torch.tensor(beta)) does */
+  float temperature;  /* 1.0 = off */
+  float top_p;        /* >= 1.0 = off */
+  int32_t top_k;      /* <= 0 = off */
+  int32_t use_contrast; /* 0: plain sampling of l (no VDD stream present) */
+  int64_t eos_token_id; /* < 0: no EOS handling (reference: eos_token_id=None) */
+  int64_t pad_token_id;
+} vdd_sample_params;
+
+VDD_API const char* vdd_last_error(void);
+VDD_API int vdd_version(void);
+
+/* ---- K8: contrastive combine + warp + softmax + sample + EOS bookkeeping, one launch -------------------------
+ * Replaces reference vcd_sample.py:185,188-202 and :257-260,285-288.
+ *   l, u, d       fp32 [B, V] (row pitch ld elements); u and/or d may be NULL.  both present: cd=(u+d)/2.
+ *   q_exp         fp32 [B, V] Exp(1) variates (torch.multinomial's own draw, see tests) or NULL => argmax.
+ *   scores_out    fp32 [B, V] post-warper scores (the reference's `scores` tuple entry) or NULL.
+ *   tokens_out    int64 [B];  unfinished int32 [B] in/out or NULL.                                              */
+VDD_API int vdd_logit_combine_sample(const float* l, const float* u, const float* d, int B, int V, int64_t ld,
+                             const vdd_sample_params* params_host, const float* q_exp, float* scores_out,
+                             int64_t* tokens_out, int32_t* unfinished, void* stream);
+
+/* ---- engine ---------------------------------------------------------------------------------------------------*/
+VDD_API int vdd_create(const vdd_config* cfg, vdd_engine** out);
+VDD_API void vdd_destroy(vdd_engine* e);
+
+/* Copy one checkpoint tensor (bf16, HF LLaVA-1.5 state-dict name, already sliced for this TP rank) into the
+ * engine's packed weight arena.  Replaces from_pretrained at reference llava/model/builder.py:102-103. */
+VDD_API int vdd_load_tensor(vdd_engine* e, const char* name, const void* src_bf16, const int64_t* shape, int ndim,
+                    void* stream);
+/* 0 when every tensor of the configured model has been loaded, else the number still missing. */
+VDD_API int vdd_missing_tensors(vdd_engine* e, char* names_out, size_t cap);
+
+/* ViT + projector (reference clip_encoder.py:39-51, multimodal_projector/builder.py:39-46):
+ * pixels bf16 [B,3,S,S] -> engine-held image features [B, P, H] fp32.  */
+VDD_API int vdd_encode_images(vdd_engine* e, const void* pixels_bf16, int B, void* stream);
+VDD_API const float* vdd_image_features(vdd_engine* e);
+
+/* Prefill of all streams in one varlen batch (reference vcd_sample.py:106-119,147-185 at step 0 +
+ * llava_arch.py:87-204).  ids_host int64 [B,T], each row holding at most one -200 sentinel.
+ * Stream order in every [S,B,...] result: main, then unk (if use_unk), then none (if use_none).
+ * with_images=0: text-only main stream (sentinel rows are an error).  Leaves last-position logits in
+ * vdd_logits().  */
+VDD_API int vdd_prefill(vdd_engine* e, const int64_t* ids_host, int B, int T, int with_images, int use_unk, int use_none,
+                int max_new_tokens, void* stream);
+/* One decode step for all S*B rows: row (s,b) consumes tokens[b].  Leaves logits in vdd_logits(). */
+VDD_API int vdd_decode_step(vdd_engine* e, const int64_t* tokens, void* stream);
+VDD_API float* vdd_logits(vdd_engine* e); /* fp32 [S, B, V] */
+VDD_API int vdd_num_streams(vdd_engine* e);
+
+/* Whole generate() with HOST buffers: encode + prefill + graph-replayed decode steps with the combine/sample
+ * kernel inside the graph.  pixels_host bf16 [B,3,S,S] (NULL => text only); q_exp [steps,B,V] device or NULL;
+ * scores_out [steps,B,V] device or NULL; tokens_out_host int64 [B, max_new_tokens]; returns the number of steps
+ * taken in *steps_out (stops early when every row has emitted EOS, reference vcd_sample.py:285-292).
+ * Synchronises the stream before returning.  */
+VDD_API int vdd_generate(vdd_engine* e, const int64_t* ids_host, int B, int T, const void* pixels_host, int use_unk,
+                 int use_none, const vdd_sample_params* params_host, int max_new_tokens, const float* q_exp,
+                 float* scores_out, int64_t* tokens_out_host, int* steps_out, void* stream);
+
+/* Tensor parallel: 128-byte NCCL unique id made on rank 0, then every rank joins. */
+VDD_API int vdd_tp_unique_id(void* id128_host);
+VDD_API int vdd_tp_init(vdd_engine* e, const void* id128_host);
+
+/* Introspection for bench.py: kernels launched since the last reset; per-phase device times of the last generate. */
+VDD_API int64_t vdd_launch_count(vdd_engine* e, int reset);
+VDD_API int vdd_last_timings(vdd_engine* e, float* vision_ms, float* prefill_ms, float* decode_ms);
+
+/* Stand-alone kernel entry points used by the unit tests and micro-benchmarks (same kernels the engine runs). */
+VDD_API int vdd_gemv(const void* w_bf16, const void* x_bf16, const float* x_f32_resid, const void* norm_w_bf16, float eps,
+             int R, int N, int K, int epilogue, float* out_f32, void* out_bf16, void* stream);
+VDD_API int vdd_gemm(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue, const void* bias_bf16,
+             const int32_t* row_map, float* out_f32, void* out_bf16, int64_t ldc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDD_H_ */

@@ -1,0 +1,70 @@
+"""`load_pretrained_model(model_path, model_base, model_name) -> (tokenizer, model, image_processor, context_len)`
+with the reference's signature and return tuple (reference experiments/llava/model/builder.py:26,148).
+
+No checkpoint can be fetched offline, so two sources are supported:
+  * "random:<name>[:seed]"  -- seeded random-init weights of the named architecture (llava-v1.5-7b / -13b / tiny);
+  * a local directory holding an HF LLaVA-1.5 checkpoint in safetensors shards (model.*, lm_head.*, vision tower).
+LoRA / 8-bit / 4-bit / MPT branches of the reference loader are out of scope.
+"""
+from __future__ import annotations
+
+import glob
+import os
+
+import torch
+
+from .config import by_name
+from .model import LlavaLlamaForCausalLM
+from .weights import state_dict_shapes, make_state_dict, _std_for
+
+
+def _load_random(model: LlavaLlamaForCausalLM, seed: int, exact: bool):
+    cfg = model.vdd_config
+    if exact:  # bit-reproducible on CPU (parity tests)
+        model.engine.load_state_dict(make_state_dict(cfg, seed))
+        return
+    g = torch.Generator(device=model.device)
+    g.manual_seed(seed)
+    for name, shape in state_dict_shapes(cfg).items():
+        if name.endswith("weight") and len(shape) == 1:
+            t = torch.ones(shape, device=model.device, dtype=torch.bfloat16)
+        else:
+            t = torch.empty(shape, device=model.device, dtype=torch.float32).normal_(0.0, float(_std_for(name, shape, cfg, -1.0)), generator=g)
+        model.engine.load_tensor(name, t)
+        del t
+    model.engine.check_complete()
+
+
+def load_pretrained_model(model_path, model_base=None, model_name=None, load_8bit=False, load_4bit=False, device_map="auto",
+                          device="cuda", tp_size=1, tp_rank=0):
+    if load_8bit or load_4bit:
+        raise NotImplementedError("bitsandbytes loading is outside the VDD path")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device == "cuda" else torch.device(device)
+    tokenizer = image_processor = None
+    if str(model_path).startswith("random:"):
+        parts = str(model_path).split(":")
+        cfg = by_name(parts[1])
+        seed = int(parts[2]) if len(parts) > 2 else 0
+        model = LlavaLlamaForCausalLM(cfg, dev, tp_size, tp_rank)
+        _load_random(model, seed, exact=cfg.name == "tiny")
+    else:
+        from safetensors import safe_open  # local checkpoint directory
+        cfg = by_name(model_name or os.path.basename(str(model_path)))
+        model = LlavaLlamaForCausalLM(cfg, dev, tp_size, tp_rank)
+        files = sorted(glob.glob(os.path.join(model_path, "*.safetensors")))
+        if not files:
+            raise FileNotFoundError(f"no *.safetensors under {model_path}")
+        for f in files:
+            with safe_open(f, framework="pt", device="cpu") as sf:
+                for k in sf.keys():
+                    model.engine.load_tensor(k, sf.get_tensor(k))
+        model.engine.check_complete()
+        try:
+            from transformers import AutoTokenizer, CLIPImageProcessor
+            tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)
+            image_processor = CLIPImageProcessor.from_pretrained(model_path)
+            model.get_vision_tower().image_processor = image_processor
+        except Exception:
+            pass
+    context_len = getattr(model.config, "max_sequence_length", 2048)  # builder.py:143-146
+    return tokenizer, model, image_processor, context_len

@@ -1,0 +1,326 @@
+// K8: contrastive logit combine + HF warpers + softmax + multinomial + EOS bookkeeping in ONE launch.
+//
+// Replaces reference vcd_utils/vcd_sample.py:185 (mean of the two debias streams), :188-194 (plausibility
+// cutoff on the raw logits and (1+a)*l - a*cd), :197-198 (Temperature -> TopK -> TopP warpers of
+// transformers/generation/logits_process.py), :201-202 (softmax + torch.multinomial == argmax(p/q), q~Exp(1)),
+// :257-260 (finished rows emit pad) and :285-288 (unfinished &= tok != eos).
+//
+// One CTA of 1024 threads per sequence; the V<=32768 scores live in registers (32 per thread), the survivors of
+// the cutoff are compacted to shared memory and bitonic-sorted there only when top-k/top-p need an order.
+// HBM-bound: algorithmic bytes per sequence = S*V*4 read (+V*4 q, +V*4 scores when requested).
+// Every fp32 operation that decides set membership is written with explicit round-to-nearest intrinsics in
+// the reference's operation order (no FMA contraction), so scores are bit-identical to torch fp32 on the same inputs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vdd {
+
+constexpr int CS_THREADS = 1024;
+constexpr int CS_ITEMS = 32;  // V <= 32768
+
+__device__ __forceinline__ int block_sum_int(int v, int* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    int t = scratch[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+__device__ __forceinline__ int block_min_int(int v, int* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    int t = scratch[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = min(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+// exclusive prefix sum of one int per thread over the 1024-thread block; *total gets the block sum
+__device__ __forceinline__ int block_exscan_int(int v, int* scratch, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) scratch[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = scratch[lane], winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    scratch[lane] = winc - w;
+    if (lane == 31) scratch[32] = winc;
+  }
+  __syncthreads();
+  *total = scratch[32];
+  return scratch[wid] + inc - v;
+}
+// inclusive SUFFIX sum of one float per thread (thread 1023 first): returns sum over threads >= tid
+__device__ __forceinline__ float block_suffix_float(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_down_sync(0xffffffffu, inc, o);
+    if (lane + o < 32) inc += t;
+  }
+  __syncthreads();
+  if (lane == 0) scratch[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    float w = scratch[lane], winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_down_sync(0xffffffffu, winc, o);
+      if (lane + o < 32) winc += t;
+    }
+    scratch[lane] = winc - w;  // sum over warps strictly after this one
+  }
+  __syncthreads();
+  return scratch[wid] + inc;
+}
+
+__global__ void __launch_bounds__(CS_THREADS, 1) combine_sample_kernel(const SampleArgs byval, const SampleArgs* dptr) {
+  extern __shared__ float sortbuf[];  // next_pow2(V) floats
+  __shared__ float redf[33];
+  __shared__ int redi[33];
+  __shared__ unsigned long long best_s;
+
+  const SampleArgs& a = dptr ? *dptr : byval;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int V = a.V;
+  const int step = a.step_ptr ? *a.step_ptr : 0;
+  const float* l = a.l + (int64_t)b * a.ld;
+  const float* u = a.u ? a.u + (int64_t)b * a.ld : nullptr;
+  const float* d = a.d ? a.d + (int64_t)b * a.ld : nullptr;
+  const int64_t so = ((int64_t)step * a.B + b) * V;
+  const float* q = a.q ? a.q + so : nullptr;
+  float* scores_out = a.scores_out ? a.scores_out + so : nullptr;
+
+  float v[CS_ITEMS];
+  // ---- pass 1: max of the raw main-stream logits (vcd_sample.py:191)
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < CS_ITEMS; ++j) {
+    const int e = j * CS_THREADS + tid;
+    v[j] = e < V ? __ldg(l + e) : -INFINITY;
+    mx = fmaxf(mx, v[j]);
+  }
+  mx = block_reduce<true>(mx, redf);
+
+  // ---- pass 2: combine + plausibility mask (vcd_sample.py:185,193-194), then temperature
+  if (a.use_contrast && (u || d)) {
+    const float cutoff = __fadd_rn(a.log_beta, mx);
+    const float a1 = a.one_plus_alpha, al = a.alpha;
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; ++j) {
+      const int e = j * CS_THREADS + tid;
+      if (e < V) {
+        float cd;
+        if (u && d) cd = __fmul_rn(__fadd_rn(__ldg(u + e), __ldg(d + e)), 0.5f);
+        else cd = u ? __ldg(u + e) : __ldg(d + e);
+        const float s = __fsub_rn(__fmul_rn(a1, v[j]), __fmul_rn(al, cd));
+        v[j] = v[j] < cutoff ? -INFINITY : s;
+      }
+    }
+  }
+  if (a.temperature != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; ++j) v[j] = __fdiv_rn(v[j], a.temperature);
+  }
+
+  // ---- warpers that need an order: TopK then TopP over the surviving (finite) scores
+  const bool want_k = a.top_k > 0 && a.top_k < V;
+  const bool want_p = a.top_p < 1.0f;
+  if (want_k || want_p) {
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; ++j) cnt += (v[j] > -INFINITY) ? 1 : 0;
+    int n_fin;
+    int off = block_exscan_int(cnt, redi, &n_fin);
+    int P = 1;
+    while (P < n_fin) P <<= 1;
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; ++j)
+      if (v[j] > -INFINITY) sortbuf[off++] = v[j];
+    for (int i = n_fin + tid; i < P; i += CS_THREADS) sortbuf[i] = -INFINITY;
+    __syncthreads();
+    // bitonic sort, descending
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int jj = k >> 1; jj > 0; jj >>= 1) {
+        for (int i = tid; i < P; i += CS_THREADS) {
+          const int x = i ^ jj;
+          if (x > i) {
+            const float A = sortbuf[i], Bv = sortbuf[x];
+            const bool desc = (i & k) == 0;
+            if ((A < Bv) == desc) { sortbuf[i] = Bv; sortbuf[x] = A; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    int n_keep = n_fin;
+    float thr = -INFINITY;  // keep score >= thr
+    if (want_k && a.top_k < n_fin) {
+      // TopKLogitsWarper: remove scores < k-th largest (ties with the k-th stay)
+      thr = sortbuf[a.top_k - 1];
+      int c = 0;
+      for (int i = tid; i < n_fin; i += CS_THREADS) c += sortbuf[i] >= thr ? 1 : 0;
+      n_keep = block_sum_int(c, redi);
+    }
+    int kept_ties = -1;  // >=0: only that many of the scores == thr survive (those with the highest index)
+    if (want_p && n_keep > 1) {
+      // TopPLogitsWarper: ascending cumulative softmax mass <= 1 - top_p is removed, the largest always stays.
+      const float m0 = sortbuf[0];
+      const int per = (n_keep + CS_THREADS - 1) / CS_THREADS;
+      const int i0 = min(tid * per, n_keep), i1 = min(i0 + per, n_keep);
+      float loc = 0.f;
+      for (int i = i1 - 1; i >= i0; --i) loc += expf(sortbuf[i] - m0);
+      const float suf_incl = block_suffix_float(loc, redf);  // sum over my chunk and all later ones
+      const float Z = block_reduce<false>(tid == 0 ? suf_incl : 0.f, redf);
+      const float lim = 1.0f - a.top_p;
+      float run = suf_incl - loc;  // mass strictly after my chunk
+      int first_removed = n_keep;
+      for (int i = i1 - 1; i >= i0; --i) {
+        run += expf(sortbuf[i] - m0);
+        if (i >= 1 && __fdiv_rn(run, Z) <= lim) first_removed = i;
+      }
+      const int n3 = block_min_int(first_removed, redi);
+      if (n3 < n_keep) {
+        thr = sortbuf[n3 - 1];
+        if (sortbuf[n3] == thr) {  // the boundary splits a run of equal scores
+          int c = 0;
+          for (int i = tid; i < n3; i += CS_THREADS) c += sortbuf[i] > thr ? 1 : 0;
+          kept_ties = n3 - block_sum_int(c, redi);
+        }
+        n_keep = n3;
+      }
+    }
+    __syncthreads();
+    if (kept_ties >= 0) {
+      // stable ascending sort puts the lower index first among equals, so the removed ties are the lowest indices
+      unsigned* bits = reinterpret_cast<unsigned*>(sortbuf);
+      for (int i = tid; i < 1024; i += CS_THREADS) bits[i] = 0u;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < CS_ITEMS; ++j) {
+        const int e = j * CS_THREADS + tid;
+        if (v[j] == thr) atomicOr(&bits[e >> 5], 1u << (e & 31));
+      }
+      __syncthreads();
+      const float above = block_suffix_float((float)__popc(bits[tid]), redf) - (float)__popc(bits[tid]);
+      __syncthreads();
+      float* above_s = sortbuf + 1024;
+      above_s[tid] = above;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < CS_ITEMS; ++j) {
+        const int e = j * CS_THREADS + tid;
+        if (v[j] == thr) {
+          const unsigned w = bits[e >> 5];
+          const unsigned hi = (e & 31) == 31 ? 0u : (w >> ((e & 31) + 1));
+          const int rank = __popc(hi) + (int)above_s[e >> 5];
+          if (rank >= kept_ties) v[j] = -INFINITY;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; ++j)
+      if (v[j] < thr) v[j] = -INFINITY;
+  }
+
+  // ---- scores (vcd_sample.py:200), softmax + multinomial (:201-202)
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < CS_ITEMS; ++j) {
+    const int e = j * CS_THREADS + tid;
+    if (e < V) {
+      if (scores_out) scores_out[e] = v[j];
+      m = fmaxf(m, v[j]);
+    }
+  }
+  m = block_reduce<true>(m, redf);
+  if (q) {  // v becomes the race key p/q in place (registers are the budget at 1024 threads)
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; ++j) {
+      v[j] = expf(v[j] - m);  // exp(-inf) = 0
+      z += v[j];
+    }
+    z = block_reduce<false>(z, redf);
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; ++j) {
+      const int e = j * CS_THREADS + tid;
+      v[j] = e < V ? __fdiv_rn(__fdiv_rn(v[j], z), __ldg(q + e)) : -1.f;
+    }
+  }
+  // argmax, lowest index on ties: pack (orderable key bits, ~index) into 64 bits
+  unsigned long long best = 0ull;
+#pragma unroll
+  for (int j = 0; j < CS_ITEMS; ++j) {
+    const int e = j * CS_THREADS + tid;
+    if (e < V) {
+      unsigned kb = __float_as_uint(v[j]);
+      kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
+      const unsigned long long p = ((unsigned long long)kb << 32) | (unsigned)(0x7fffffff - e);
+      best = p > best ? p : best;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+    best = t > best ? t : best;
+  }
+  if (tid == 0) best_s = 0ull;
+  __syncthreads();
+  if ((tid & 31) == 0) atomicMax(&best_s, best);
+  __syncthreads();
+  if (tid == 0) {
+    long long tok = 0x7fffffff - (int)(best_s & 0xffffffffull);
+    // finished rows emit pad (vcd_sample.py:257-260), then the unfinished mask drops rows that hit EOS (:285-288)
+    if (a.eos >= 0 && a.unfinished) {
+      const int unf = a.unfinished[b];
+      tok = tok * unf + a.pad * (1 - unf);
+      a.unfinished[b] = (unf != 0 && tok != a.eos) ? 1 : 0;
+    }
+    if (a.tokens_out) a.tokens_out[b] = tok;
+    if (a.seq_out) a.seq_out[(int64_t)b * a.seq_ld + step] = tok;
+  }
+}
+
+cudaError_t launch_combine_sample(const SampleArgs& args, const SampleArgs* dptr, int B, int V, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(combine_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int P = 1;
+  while (P < V) P <<= 1;
+  if (P < 2048) P = 2048;  // the tie-split path uses 2048 words
+  combine_sample_kernel<<<B, CS_THREADS, (size_t)P * 4, stream>>>(args, dptr);
+  return cudaGetLastError();
+}
+
+}  // namespace vdd

@@ -1,0 +1,967 @@
+// libvdd engine: weight arena, per-generation row/stream plan, prefill / decode orchestration, CUDA-graph replay of
+// the decode step with the combine+sample kernel inside, and the C ABI of include/vdd.h.
+//
+// What it stands in for in the reference (all Python there):
+//   sample() loop + per-stream model_kwargs bookkeeping     vcd_utils/vcd_sample.py:93-299
+//   LlavaLlamaForCausalLM.forward / prepare_inputs_*         experiments/llava/model/language_model/llava_llama.py:58-174
+//   prepare_inputs_labels_for_multimodal (image splice)      experiments/llava/model/llava_arch.py:87-204
+//   CLIPVisionTower.forward + mm_projector                   multimodal_encoder/clip_encoder.py:39-51, multimodal_projector/builder.py:39-46
+// The reference runs S = 1 + {1,2} separate forwards per token with separate KV caches; here every stream of every
+// sequence is a ROW of one fused batch (row = stream*B + b), so each weight byte is read once per token.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vdd.h"
+#include "kernels.h"
+
+using namespace vdd;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t _e = (call);                                                                              \
+    if (_e != cudaSuccess) return fail(VDD_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" const char* vdd_last_error(void) { return g_err; }
+extern "C" int vdd_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------ NCCL (loaded lazily; TP only)
+typedef struct ncclComm* ncclComm_t;
+struct NcclId { char b[128]; };  // ncclUniqueId, passed by value
+struct NcclApi {
+  void* lib = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclId, int) = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static bool nccl_load() {
+  if (g_nccl.lib) return true;
+  const char* names[] = {getenv("VDD_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n) continue;
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return false;
+  *(void**)&g_nccl.GetUniqueId = dlsym(g_nccl.lib, "ncclGetUniqueId");
+  *(void**)&g_nccl.CommInitRank = dlsym(g_nccl.lib, "ncclCommInitRank");
+  *(void**)&g_nccl.AllReduce = dlsym(g_nccl.lib, "ncclAllReduce");
+  *(void**)&g_nccl.AllGather = dlsym(g_nccl.lib, "ncclAllGather");
+  *(void**)&g_nccl.CommDestroy = dlsym(g_nccl.lib, "ncclCommDestroy");
+  *(void**)&g_nccl.GetErrorString = dlsym(g_nccl.lib, "ncclGetErrorString");
+  return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.AllGather;
+}
+
+// ------------------------------------------------------------------------------------------------ engine state
+struct Slot {
+  void* ptr = nullptr;
+  int64_t rows = 0, cols = 0;     // expected source shape (flattened 2D)
+  int64_t dst_pitch = 0;          // destination row pitch in elements (>= cols)
+  bool loaded = false, ignore = false;
+};
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+struct LayerW {
+  void *wqkv, *wo, *wgu, *wdown, *ln1, *ln2;
+};
+struct VLayerW {
+  void *ln1w, *ln1b, *wqkv, *bqkv, *wo, *bo, *ln2w, *ln2b, *fc1, *b1, *fc2, *b2;
+};
+
+struct vdd_engine {
+  vdd_config c;
+  int D = 128, heads_l = 0, Hl = 0, Il = 0, Vl = 0, NP = 0, Kpad = 0, VD = 64;
+  int num_sms = 148;
+  bool use_pdl = true, use_graph = true;
+  // weights
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::map<std::string, Slot> slots;
+  std::map<std::string, int> parts;  // arrivals per fused slot
+  std::vector<LayerW> lw;
+  std::vector<VLayerW> vw;
+  void *embed, *final_norm, *lm_head;
+  void *patch_w, *cls, *vpos, *preln_w, *preln_b, *pj_w1, *pj_b1, *pj_w2, *pj_b2;
+  float *rope_cos = nullptr, *rope_sin = nullptr;
+  // workspaces
+  DevBuf resid, xn, qkv, qb, attn, hbuf, meta, kv, logits, logits_tp, dec_f32, dec_bf16, part, img_feats, vis, pix, misc, tp_tmp;
+  // per-generation plan
+  int B = 0, T = 0, S = 0, R = 0, Mtot = 0, max_new = 0, max_len = 0, max_splits = 1;
+  int64_t kv_layer_stride = 0;
+  int32_t *d_tok = nullptr, *d_img_row = nullptr, *d_row_seq = nullptr, *d_row_pos = nullptr, *d_kv_cap = nullptr,
+          *d_pos = nullptr, *d_last_rows = nullptr, *d_seqlen = nullptr, *d_q_row0 = nullptr, *d_step = nullptr,
+          *d_unfinished = nullptr, *d_counters = nullptr;
+  int64_t *d_kv_off = nullptr, *d_head_stride = nullptr, *d_tokens = nullptr, *d_seq_out = nullptr;
+  SampleArgs* d_sargs = nullptr;
+  bool prefilled = false;
+  int image_B = 0;
+  // decode buffers (views into dec_f32 / dec_bf16)
+  float *resid_d = nullptr, *qkv_d = nullptr, *part_o = nullptr, *part_ml = nullptr, *tp_part = nullptr;
+  void *attn_d = nullptr, *h_d = nullptr, *xn_d = nullptr;
+  // graph cache
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_key = 0;
+  int graph_nodes = 0;
+  // TP
+  ncclComm_t comm = nullptr;
+  // stats
+  int64_t launches = 0;
+  float t_vision = 0, t_prefill = 0, t_decode = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* pinned = nullptr;  // small pinned scratch
+  size_t pinned_bytes = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int ensure(vdd_engine* e, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes) return VDD_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.bytes = 0;
+  bytes = align_up(bytes + bytes / 8, 1 << 20);
+  CK(cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  if (e->graph_exec) {  // captured pointers are stale now
+    cudaGraphExecDestroy(e->graph_exec);
+    e->graph_exec = nullptr;
+  }
+  return VDD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ create
+static void add_slot(vdd_engine* e, std::vector<std::pair<std::string, size_t>>& order, const std::string& name,
+                     int64_t rows, int64_t cols, int64_t pitch = 0) {
+  Slot s;
+  s.rows = rows;
+  s.cols = cols;
+  s.dst_pitch = pitch ? pitch : cols;
+  e->slots[name] = s;
+  order.push_back({name, (size_t)rows * s.dst_pitch * 2});
+}
+
+extern "C" int vdd_create(const vdd_config* cfg, vdd_engine** out) {
+  if (!cfg || !out) return fail(VDD_ERR_ARG, "null argument");
+  int dev_count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&dev_count);
+  if (ce != cudaSuccess || dev_count == 0)
+    return fail(VDD_ERR_CUDA, "libvdd needs a CUDA device (sm_100a); none visible: %s", cudaGetErrorString(ce));
+  const vdd_config& c = *cfg;
+  if (c.num_heads <= 0 || c.hidden_size % c.num_heads || c.hidden_size / c.num_heads != 128)
+    return fail(VDD_ERR_UNSUPPORTED, "head_dim must be 128 (LLaMA-family LLaVA-1.5)");
+  if (c.v_hidden / c.v_heads != 64) return fail(VDD_ERR_UNSUPPORTED, "vision head_dim must be 64 (CLIP ViT-L/14)");
+  const int tp = c.tp_size < 1 ? 1 : c.tp_size;
+  if (c.num_heads % tp || c.intermediate_size % tp || c.vocab_size % tp)
+    return fail(VDD_ERR_ARG, "heads/intermediate/vocab must divide by tp_size");
+  if ((c.intermediate_size / tp) % 8 || (c.vocab_size / tp) % 16 || c.hidden_size % 64)
+    return fail(VDD_ERR_UNSUPPORTED, "local dims must be multiples of 8/16/64");
+  vdd_engine* e = new vdd_engine();
+  e->c = c;
+  e->c.tp_size = tp;
+  e->heads_l = c.num_heads / tp;
+  e->Hl = e->heads_l * 128;
+  e->Il = c.intermediate_size / tp;
+  e->Vl = c.vocab_size / tp;
+  e->NP = (c.image_size / c.patch_size) * (c.image_size / c.patch_size);
+  e->Kpad = (int)align_up((size_t)3 * c.patch_size * c.patch_size, 64);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  e->use_pdl = getenv("VDD_NO_PDL") == nullptr;
+  e->use_graph = getenv("VDD_NO_GRAPH") == nullptr;
+
+  const int64_t H = c.hidden_size, VH = c.v_hidden, VI = c.v_intermediate;
+  std::vector<std::pair<std::string, size_t>> order;
+  add_slot(e, order, "model.embed_tokens.weight", c.vocab_size, H);
+  add_slot(e, order, "model.norm.weight", 1, H);
+  add_slot(e, order, "lm_head.weight", e->Vl, H);
+  for (int i = 0; i < c.num_layers; ++i) {
+    const std::string p = "model.layers." + std::to_string(i) + ".";
+    add_slot(e, order, p + "qkv", 3 * e->Hl, H);
+    add_slot(e, order, p + "self_attn.o_proj.weight", H, e->Hl);
+    add_slot(e, order, p + "gate_up", 2 * e->Il, H);
+    add_slot(e, order, p + "mlp.down_proj.weight", H, e->Il);
+    add_slot(e, order, p + "input_layernorm.weight", 1, H);
+    add_slot(e, order, p + "post_attention_layernorm.weight", 1, H);
+  }
+  add_slot(e, order, "model.mm_projector.0.weight", H, VH);
+  add_slot(e, order, "model.mm_projector.0.bias", 1, H);
+  add_slot(e, order, "model.mm_projector.2.weight", H, H);
+  add_slot(e, order, "model.mm_projector.2.bias", 1, H);
+  const std::string vt = "model.vision_tower.vision_tower.vision_model.";
+  add_slot(e, order, vt + "embeddings.class_embedding", 1, VH);
+  add_slot(e, order, vt + "embeddings.patch_embedding.weight", VH, 3 * c.patch_size * c.patch_size, e->Kpad);
+  add_slot(e, order, vt + "embeddings.position_embedding.weight", e->NP + 1, VH);
+  add_slot(e, order, vt + "pre_layrnorm.weight", 1, VH);
+  add_slot(e, order, vt + "pre_layrnorm.bias", 1, VH);
+  for (int i = 0; i < c.v_layers_used; ++i) {
+    const std::string p = vt + "encoder.layers." + std::to_string(i) + ".";
+    add_slot(e, order, p + "qkv.weight", 3 * VH, VH);
+    add_slot(e, order, p + "qkv.bias", 1, 3 * VH);
+    add_slot(e, order, p + "self_attn.out_proj.weight", VH, VH);
+    add_slot(e, order, p + "self_attn.out_proj.bias", 1, VH);
+    add_slot(e, order, p + "layer_norm1.weight", 1, VH);
+    add_slot(e, order, p + "layer_norm1.bias", 1, VH);
+    add_slot(e, order, p + "layer_norm2.weight", 1, VH);
+    add_slot(e, order, p + "layer_norm2.bias", 1, VH);
+    add_slot(e, order, p + "mlp.fc1.weight", VI, VH);
+    add_slot(e, order, p + "mlp.fc1.bias", 1, VI);
+    add_slot(e, order, p + "mlp.fc2.weight", VH, VI);
+    add_slot(e, order, p + "mlp.fc2.bias", 1, VH);
+  }
+  size_t total = 0;
+  for (auto& o : order) total += align_up(o.second, 256);
+  cudaError_t me = cudaMalloc(&e->arena, total);
+  if (me != cudaSuccess) {
+    delete e;
+    return fail(VDD_ERR_CUDA, "cudaMalloc(%zu bytes of weights): %s", total, cudaGetErrorString(me));
+  }
+  cudaMemset(e->arena, 0, total);
+  e->arena_bytes = total;
+  size_t off = 0;
+  for (auto& o : order) {
+    e->slots[o.first].ptr = (char*)e->arena + off;
+    off += align_up(o.second, 256);
+  }
+  auto P = [&](const std::string& n) { return e->slots[n].ptr; };
+  e->embed = P("model.embed_tokens.weight");
+  e->final_norm = P("model.norm.weight");
+  e->lm_head = P("lm_head.weight");
+  e->lw.resize(c.num_layers);
+  for (int i = 0; i < c.num_layers; ++i) {
+    const std::string p = "model.layers." + std::to_string(i) + ".";
+    e->lw[i] = {P(p + "qkv"), P(p + "self_attn.o_proj.weight"), P(p + "gate_up"), P(p + "mlp.down_proj.weight"),
+                P(p + "input_layernorm.weight"), P(p + "post_attention_layernorm.weight")};
+  }
+  e->pj_w1 = P("model.mm_projector.0.weight");
+  e->pj_b1 = P("model.mm_projector.0.bias");
+  e->pj_w2 = P("model.mm_projector.2.weight");
+  e->pj_b2 = P("model.mm_projector.2.bias");
+  e->cls = P(vt + "embeddings.class_embedding");
+  e->patch_w = P(vt + "embeddings.patch_embedding.weight");
+  e->vpos = P(vt + "embeddings.position_embedding.weight");
+  e->preln_w = P(vt + "pre_layrnorm.weight");
+  e->preln_b = P(vt + "pre_layrnorm.bias");
+  e->vw.resize(c.v_layers_used);
+  for (int i = 0; i < c.v_layers_used; ++i) {
+    const std::string p = vt + "encoder.layers." + std::to_string(i) + ".";
+    e->vw[i] = {P(p + "layer_norm1.weight"), P(p + "layer_norm1.bias"), P(p + "qkv.weight"), P(p + "qkv.bias"),
+                P(p + "self_attn.out_proj.weight"), P(p + "self_attn.out_proj.bias"), P(p + "layer_norm2.weight"),
+                P(p + "layer_norm2.bias"), P(p + "mlp.fc1.weight"), P(p + "mlp.fc1.bias"), P(p + "mlp.fc2.weight"),
+                P(p + "mlp.fc2.bias")};
+  }
+  // RoPE table, HF LlamaRotaryEmbedding arithmetic: inv_freq fp32, angle = pos * inv_freq in fp32, cos/sin of it
+  {
+    const int half = 64, mp = c.max_position;
+    std::vector<float> hc((size_t)mp * half), hs((size_t)mp * half);
+    for (int i = 0; i < half; ++i) {
+      const float inv = 1.0f / powf(c.rope_theta, (float)(2 * i) / 128.0f);
+      for (int p = 0; p < mp; ++p) {
+        const float ang = (float)p * inv;
+        hc[(size_t)p * half + i] = cosf(ang);
+        hs[(size_t)p * half + i] = sinf(ang);
+      }
+    }
+    cudaMalloc(&e->rope_cos, hc.size() * 4);
+    cudaMalloc(&e->rope_sin, hs.size() * 4);
+    cudaMemcpy(e->rope_cos, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(e->rope_sin, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice);
+  }
+  for (int i = 0; i < 4; ++i) cudaEventCreate(&e->ev[i]);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    delete e;
+    return fail(VDD_ERR_CUDA, "vdd_create: %s", cudaGetErrorString(le));
+  }
+  *out = e;
+  return VDD_OK;
+}
+
+extern "C" void vdd_destroy(vdd_engine* e) {
+  if (!e) return;
+  cudaDeviceSynchronize();
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  DevBuf* bufs[] = {&e->resid, &e->xn, &e->qkv, &e->qb, &e->attn, &e->hbuf, &e->meta, &e->kv, &e->logits, &e->logits_tp,
+                    &e->dec_f32, &e->dec_bf16, &e->part, &e->img_feats, &e->vis, &e->pix, &e->misc, &e->tp_tmp};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (e->arena) cudaFree(e->arena);
+  if (e->rope_cos) cudaFree(e->rope_cos);
+  if (e->rope_sin) cudaFree(e->rope_sin);
+  if (e->pinned) cudaFreeHost(e->pinned);
+  for (int i = 0; i < 4; ++i)
+    if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  delete e;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+static bool ends_with(const std::string& s, const char* suf) {
+  const size_t n = strlen(suf);
+  return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+extern "C" int vdd_load_tensor(vdd_engine* e, const char* name_c, const void* src, const int64_t* shape, int ndim,
+                               void* stream_v) {
+  if (!e || !name_c || !src || !shape || ndim < 1) return fail(VDD_ERR_ARG, "null argument");
+  cudaStream_t st = (cudaStream_t)stream_v;
+  std::string name(name_c);
+  int64_t rows = ndim == 1 ? 1 : shape[0], cols = 1;
+  for (int i = (ndim == 1 ? 0 : 1); i < ndim; ++i) cols *= shape[i];
+  // fused / repacked destinations
+  std::string key = name;
+  int64_t row_off = 0, row_step = 1, col_off = 0, exp_rows = -1, exp_cols = -1;
+  int parts_needed = 0;
+  const std::string vt = "model.vision_tower.vision_tower.vision_model.";
+  if (name.compare(0, 13, "model.layers.") == 0) {
+    const std::string pre = name.substr(0, name.find('.', 13) + 1);
+    const char* qkvn[3] = {"self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight"};
+    for (int i = 0; i < 3; ++i)
+      if (ends_with(name, qkvn[i])) {
+        key = pre + "qkv"; row_off = (int64_t)i * e->Hl; exp_rows = e->Hl; exp_cols = e->c.hidden_size; parts_needed = 3;
+      }
+    // gate and up rows are interleaved (2j = gate_j, 2j+1 = up_j) so SwiGLU is an epilogue of one projection
+    if (ends_with(name, "mlp.gate_proj.weight")) { key = pre + "gate_up"; row_off = 0; row_step = 2; exp_rows = e->Il; exp_cols = e->c.hidden_size; parts_needed = 2; }
+    if (ends_with(name, "mlp.up_proj.weight")) { key = pre + "gate_up"; row_off = 1; row_step = 2; exp_rows = e->Il; exp_cols = e->c.hidden_size; parts_needed = 2; }
+  } else if (name.compare(0, vt.size(), vt) == 0 && name.find("encoder.layers.") != std::string::npos) {
+    const size_t lp = name.find("encoder.layers.") + 15;
+    const int li = atoi(name.c_str() + lp);
+    if (li >= e->c.v_layers_used) return VDD_OK;  // layer never contributes (select_layer=-2, clip_encoder.py:30)
+    const std::string pre = name.substr(0, name.find('.', lp) + 1);
+    const char* n3[3] = {"self_attn.q_proj.", "self_attn.k_proj.", "self_attn.v_proj."};
+    for (int i = 0; i < 3; ++i) {
+      if (name.find(n3[i]) != std::string::npos) {
+        parts_needed = 3;
+        if (ends_with(name, "weight")) { key = pre + "qkv.weight"; row_off = (int64_t)i * e->c.v_hidden; exp_rows = e->c.v_hidden; exp_cols = e->c.v_hidden; }
+        else { key = pre + "qkv.bias"; col_off = (int64_t)i * e->c.v_hidden; exp_rows = 1; exp_cols = e->c.v_hidden; }
+      }
+    }
+  } else if (name.compare(0, vt.size(), vt) == 0 && name.find("post_layernorm") != std::string::npos) {
+    return VDD_OK;  // unused by feature_select (clip_encoder.py:29-37)
+  }
+  auto it = e->slots.find(key);
+  if (it == e->slots.end()) return fail(VDD_ERR_ARG, "unknown tensor '%s'", name_c);
+  Slot& s = it->second;
+  if (exp_rows < 0) { exp_rows = s.rows; exp_cols = s.cols; }
+  if (rows * cols != exp_rows * exp_cols)
+    return fail(VDD_ERR_ARG, "tensor '%s': got %lld elements, expected %lld x %lld", name_c, (long long)(rows * cols),
+                (long long)exp_rows, (long long)exp_cols);
+  char* dst = (char*)s.ptr + (row_off * s.dst_pitch + col_off) * 2;
+  CK(cudaMemcpy2DAsync(dst, (size_t)s.dst_pitch * row_step * 2, src, (size_t)exp_cols * 2, (size_t)exp_cols * 2, (size_t)exp_rows,
+                       cudaMemcpyDeviceToDevice, st));
+  if (parts_needed == 0) s.loaded = true;
+  else if (++e->parts[key] >= parts_needed) s.loaded = true;
+  return VDD_OK;
+}
+
+extern "C" int vdd_missing_tensors(vdd_engine* e, char* names_out, size_t cap) {
+  int n = 0;
+  std::string acc;
+  for (auto& kv : e->slots)
+    if (!kv.second.loaded) {
+      ++n;
+      if (acc.size() < 900) acc += kv.first + ";";
+    }
+  if (names_out && cap) snprintf(names_out, cap, "%s", acc.c_str());
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------ launch helpers
+#define LK(e, call)                                                                                        \
+  do {                                                                                                     \
+    cudaError_t _e = (call);                                                                               \
+    (e)->launches++;                                                                                       \
+    if (_e != cudaSuccess) return fail(VDD_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+static int tp_allreduce_add(vdd_engine* e, float* partial, float* resid, int64_t n, cudaStream_t st) {
+  // row-parallel projection: sum the per-rank partials over NVLink, then resid += sum
+  int r = g_nccl.AllReduce(partial, partial, (size_t)n, /*ncclFloat*/ 7, /*ncclSum*/ 0, e->comm, st);
+  if (r != 0) return fail(VDD_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  e->launches++;
+  LK(e, launch_add_rows(resid, partial, n, st));
+  return VDD_OK;
+}
+
+static int do_gemm(vdd_engine* e, const void* a, const void* w, int M, int N, int K, int mode, const void* bias,
+                   const int32_t* row_map, float* of32, void* obf16, int64_t ldc, cudaStream_t st) {
+  GemmArgs g{a, w, M, N, K, mode, bias, row_map, of32, obf16, ldc};
+  cudaError_t ce = launch_gemm(g, st);
+  e->launches++;
+  if (ce != cudaSuccess)
+    return fail(VDD_ERR_CUDA, "gemm M=%d N=%d K=%d: %s %s", M, N, K, cudaGetErrorString(ce), gemm_init_error() ? gemm_init_error() : "");
+  return VDD_OK;
+}
+#define RC(x)               \
+  do {                      \
+    int _r = (x);           \
+    if (_r != VDD_OK) return _r; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ vision
+extern "C" int vdd_encode_images(vdd_engine* e, const void* pixels, int B, void* stream_v) {
+  if (!e || !pixels || B <= 0) return fail(VDD_ERR_ARG, "bad argument");
+  if (vdd_missing_tensors(e, nullptr, 0)) {
+    char buf[512];
+    vdd_missing_tensors(e, buf, sizeof buf);
+    return fail(VDD_ERR_STATE, "weights missing: %s", buf);
+  }
+  cudaStream_t st = (cudaStream_t)stream_v;
+  const vdd_config& c = e->c;
+  const int NP = e->NP, VH = c.v_hidden, VI = c.v_intermediate, H = c.hidden_size, NT = NP + 1;
+  const int Mp = B * NP, Mv = B * NT;
+  // carve the vision workspace
+  size_t o = 0;
+  auto carve = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+  const size_t o_patch = carve((size_t)Mp * e->Kpad * 2), o_pout = carve((size_t)Mp * VH * 4), o_res = carve((size_t)Mv * VH * 4),
+               o_xn = carve((size_t)Mv * VH * 2), o_qkv = carve((size_t)Mv * 3 * VH * 2), o_att = carve((size_t)Mv * VH * 2),
+               o_h = carve((size_t)Mv * VI * 2), o_pin = carve((size_t)Mp * VH * 2), o_ph = carve((size_t)Mp * H * 2),
+               o_idx = carve((size_t)Mp * 4), o_meta = carve((size_t)B * 32);
+  RC(ensure(e, e->vis, o));
+  RC(ensure(e, e->img_feats, (size_t)Mp * H * 4));
+  char* base = (char*)e->vis.p;
+  void* patches = base + o_patch; float* pout = (float*)(base + o_pout); float* res = (float*)(base + o_res);
+  void* xn = base + o_xn; void* qkv = base + o_qkv; void* att = base + o_att; void* hb = base + o_h;
+  void* pin = base + o_pin; void* ph = base + o_ph; int32_t* idx = (int32_t*)(base + o_idx);
+  // per-image attention metadata + feature-select row list (drop CLS: clip_encoder.py:33-34)
+  std::vector<int32_t> hidx(Mp), hq0(B), hlen(B);
+  std::vector<int64_t> hoff(B), hhs(B);
+  for (int b = 0; b < B; ++b) {
+    hq0[b] = b * NT; hlen[b] = NT; hoff[b] = (int64_t)b * NT * 3 * VH; hhs[b] = 64;
+    for (int p = 0; p < NP; ++p) hidx[(size_t)b * NP + p] = b * NT + 1 + p;
+  }
+  char* meta = base + o_meta;
+  int32_t* d_q0 = (int32_t*)meta; int32_t* d_len = d_q0 + B; int64_t* d_off = (int64_t*)(meta + (size_t)B * 8);
+  int64_t* d_hs = d_off + B;
+  CK(cudaMemcpyAsync(idx, hidx.data(), (size_t)Mp * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_q0, hq0.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_len, hlen.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_off, hoff.data(), (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_hs, hhs.data(), (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // host vectors go out of scope
+
+  LK(e, launch_im2col(pixels, patches, B, c.image_size, c.patch_size, e->Kpad, st));
+  RC(do_gemm(e, patches, e->patch_w, Mp, VH, e->Kpad, GEMM_OUT_F32, nullptr, nullptr, pout, nullptr, VH, st));
+  LK(e, launch_vit_embed(pout, e->cls, e->vpos, res, B, NP, VH, st));
+  LK(e, launch_layernorm(res, e->preln_w, e->preln_b, c.v_ln_eps, nullptr, res, Mv, VH, nullptr, st));
+  for (int l = 0; l < c.v_layers_used; ++l) {
+    const VLayerW& w = e->vw[l];
+    LK(e, launch_layernorm(res, w.ln1w, w.ln1b, c.v_ln_eps, xn, nullptr, Mv, VH, nullptr, st));
+    RC(do_gemm(e, xn, w.wqkv, Mv, 3 * VH, VH, GEMM_OUT_BF16, w.bqkv, nullptr, nullptr, qkv, 3 * VH, st));
+    PrefillAttnArgs pa{};
+    pa.q = qkv; pa.q_ld = 3 * VH;
+    pa.k = (char*)qkv + (size_t)VH * 2; pa.v = (char*)qkv + (size_t)2 * VH * 2;
+    pa.k_off = d_off; pa.k_head_stride = d_hs; pa.k_tok_stride = 3 * VH;
+    pa.q_row0 = d_q0; pa.seqlen = d_len; pa.out = att; pa.out_ld = VH;
+    pa.nseq = B; pa.heads = c.v_heads; pa.max_seqlen = NT; pa.causal = 0; pa.head_dim = 64; pa.scale = 0.125f;
+    LK(e, launch_prefill_attn(pa, st));
+    RC(do_gemm(e, att, w.wo, Mv, VH, VH, GEMM_OUT_ADD_F32, w.bo, nullptr, res, nullptr, VH, st));
+    LK(e, launch_layernorm(res, w.ln2w, w.ln2b, c.v_ln_eps, xn, nullptr, Mv, VH, nullptr, st));
+    RC(do_gemm(e, xn, w.fc1, Mv, VI, VH, GEMM_OUT_BF16_QGELU, w.b1, nullptr, nullptr, hb, VI, st));
+    RC(do_gemm(e, hb, w.fc2, Mv, VH, VI, GEMM_OUT_ADD_F32, w.b2, nullptr, res, nullptr, VH, st));
+  }
+  // feature_select('patch') then mm_projector (mlp2x_gelu)
+  LK(e, launch_cast_rows_bf16(res, pin, Mp, VH, idx, st));
+  RC(do_gemm(e, pin, e->pj_w1, Mp, H, VH, GEMM_OUT_BF16_GELU, e->pj_b1, nullptr, nullptr, ph, H, st));
+  RC(do_gemm(e, ph, e->pj_w2, Mp, H, H, GEMM_OUT_F32, e->pj_b2, nullptr, (float*)e->img_feats.p, nullptr, H, st));
+  e->image_B = B;
+  return VDD_OK;
+}
+extern "C" const float* vdd_image_features(vdd_engine* e) { return e ? (const float*)e->img_feats.p : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ prefill
+static int tp_gather_logits(vdd_engine* e, cudaStream_t st);
+
+extern "C" int vdd_prefill(vdd_engine* e, const int64_t* ids, int B, int T, int with_images, int use_unk, int use_none,
+                           int max_new, void* stream_v) {
+  if (!e || !ids || B <= 0 || T <= 0 || max_new < 1) return fail(VDD_ERR_ARG, "bad argument");
+  if (vdd_missing_tensors(e, nullptr, 0)) {
+    char buf[512];
+    vdd_missing_tensors(e, buf, sizeof buf);
+    return fail(VDD_ERR_STATE, "weights missing: %s", buf);
+  }
+  cudaStream_t st = (cudaStream_t)stream_v;
+  const vdd_config& c = e->c;
+  const int H = c.hidden_size, NP = e->NP, L = c.num_layers, Hl = e->Hl, Il = e->Il;
+  const int S = 1 + (use_unk ? 1 : 0) + (use_none ? 1 : 0), R = S * B;
+  if (with_images && e->image_B != B) return fail(VDD_ERR_STATE, "vdd_encode_images(B=%d) must precede prefill(B=%d)", e->image_B, B);
+
+  // ---- row plan (vcd_sample.py:152-160: unk = sentinel -> token 0; none = sentinel deleted; main = 576 image rows)
+  std::vector<int> kinds;  // 0 main, 1 unk, 2 none
+  kinds.push_back(0);
+  if (use_unk) kinds.push_back(1);
+  if (use_none) kinds.push_back(2);
+  std::vector<int32_t> tok, img_row, row_seq, row_pos, seqlen(R), q_row0(R), kv_cap(R), last_rows(R);
+  std::vector<int64_t> kv_off(R), head_stride(R);
+  int64_t kv_total = 0;
+  int max_len = 0;
+  for (int s = 0; s < S; ++s) {
+    for (int b = 0; b < B; ++b) {
+      const int q = s * B + b;
+      q_row0[q] = (int32_t)tok.size();
+      int nsent = 0, pos = 0;
+      for (int t = 0; t < T; ++t) {
+        const int64_t id = ids[(size_t)b * T + t];
+        if (id == VDD_IMAGE_TOKEN_INDEX) {
+          ++nsent;
+          if (nsent > 1) return fail(VDD_ERR_UNSUPPORTED, "row %d holds more than one image sentinel", b);
+          if (kinds[s] == 0) {
+            if (!with_images) return fail(VDD_ERR_ARG, "row %d has an image sentinel but no images were given", b);
+            for (int p = 0; p < NP; ++p) {
+              tok.push_back(-1); img_row.push_back(b * NP + p); row_seq.push_back(q); row_pos.push_back(pos++);
+            }
+          } else if (kinds[s] == 1) {
+            tok.push_back(0); img_row.push_back(-1); row_seq.push_back(q); row_pos.push_back(pos++);
+          }  // kind 2: dropped
+        } else {
+          if (id < 0 || id >= c.vocab_size) return fail(VDD_ERR_ARG, "token id %lld out of range", (long long)id);
+          tok.push_back((int32_t)id); img_row.push_back(-1); row_seq.push_back(q); row_pos.push_back(pos++);
+        }
+      }
+      if (pos == 0) return fail(VDD_ERR_ARG, "empty sequence");
+      seqlen[q] = pos;
+      last_rows[q] = q_row0[q] + pos - 1;
+      kv_cap[q] = (int32_t)align_up((size_t)pos + max_new, 8);
+      if (kv_cap[q] > c.max_position) return fail(VDD_ERR_ARG, "prompt %d + %d new tokens exceeds max_position %d", pos, max_new, c.max_position);
+      kv_off[q] = kv_total;
+      head_stride[q] = (int64_t)kv_cap[q] * 128;
+      kv_total += (int64_t)kv_cap[q] * Hl;
+      if (pos > max_len) max_len = pos;
+    }
+  }
+  const int Mtot = (int)tok.size();
+  e->B = B; e->T = T; e->S = S; e->R = R; e->Mtot = Mtot; e->max_new = max_new; e->max_len = max_len;
+  e->kv_layer_stride = kv_total;
+  e->max_splits = (max_len + max_new + 127) / 128;
+
+  // ---- buffers
+  RC(ensure(e, e->resid, (size_t)Mtot * H * 4));
+  RC(ensure(e, e->xn, (size_t)Mtot * H * 2));
+  RC(ensure(e, e->qkv, (size_t)Mtot * 3 * Hl * 4));
+  RC(ensure(e, e->qb, (size_t)Mtot * Hl * 2));
+  RC(ensure(e, e->attn, (size_t)Mtot * Hl * 2));
+  RC(ensure(e, e->hbuf, (size_t)Mtot * Il * 2));
+  RC(ensure(e, e->kv, (size_t)2 * L * kv_total * 2));
+  RC(ensure(e, e->logits, (size_t)R * c.vocab_size * 4));
+  if (c.tp_size > 1) {
+    RC(ensure(e, e->logits_tp, (size_t)R * c.vocab_size * 4));
+    RC(ensure(e, e->tp_tmp, (size_t)(Mtot > R ? Mtot : R) * H * 4));
+    RC(ensure(e, e->misc, (size_t)R * c.vocab_size * 4));
+  }
+  {
+    size_t o = 0;
+    auto carve = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+    const size_t o_res = carve((size_t)R * H * 4), o_qkv = carve((size_t)R * 3 * Hl * 4),
+                 o_po = carve((size_t)R * e->heads_l * e->max_splits * 128 * 4), o_pm = carve((size_t)R * e->heads_l * e->max_splits * 8);
+    RC(ensure(e, e->dec_f32, o));
+    char* b = (char*)e->dec_f32.p;
+    e->resid_d = (float*)(b + o_res); e->qkv_d = (float*)(b + o_qkv); e->part_o = (float*)(b + o_po); e->part_ml = (float*)(b + o_pm);
+    o = 0;
+    const size_t o_at = carve((size_t)R * Hl * 2), o_h = carve((size_t)R * Il * 2), o_xn = carve((size_t)R * H * 2);
+    RC(ensure(e, e->dec_bf16, o));
+    b = (char*)e->dec_bf16.p;
+    e->attn_d = b + o_at; e->h_d = b + o_h; e->xn_d = b + o_xn;
+  }
+  {
+    size_t o = 0;
+    auto carve = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+    const size_t o_tok = carve((size_t)Mtot * 4), o_img = carve((size_t)Mtot * 4), o_rs = carve((size_t)Mtot * 4), o_rp = carve((size_t)Mtot * 4),
+                 o_cap = carve((size_t)R * 4), o_pos = carve((size_t)R * 4), o_last = carve((size_t)R * 4), o_len = carve((size_t)R * 4),
+                 o_q0 = carve((size_t)R * 4), o_step = carve(256), o_unf = carve((size_t)B * 4), o_cnt = carve((size_t)R * e->heads_l * 4),
+                 o_off = carve((size_t)R * 8), o_hs = carve((size_t)R * 8), o_tokens = carve((size_t)B * 8),
+                 o_seq = carve((size_t)B * max_new * 8), o_sa = carve(sizeof(SampleArgs));
+    RC(ensure(e, e->meta, o));
+    char* b = (char*)e->meta.p;
+    e->d_tok = (int32_t*)(b + o_tok); e->d_img_row = (int32_t*)(b + o_img); e->d_row_seq = (int32_t*)(b + o_rs);
+    e->d_row_pos = (int32_t*)(b + o_rp); e->d_kv_cap = (int32_t*)(b + o_cap); e->d_pos = (int32_t*)(b + o_pos);
+    e->d_last_rows = (int32_t*)(b + o_last); e->d_seqlen = (int32_t*)(b + o_len); e->d_q_row0 = (int32_t*)(b + o_q0);
+    e->d_step = (int32_t*)(b + o_step); e->d_unfinished = (int32_t*)(b + o_unf); e->d_counters = (int32_t*)(b + o_cnt);
+    e->d_kv_off = (int64_t*)(b + o_off); e->d_head_stride = (int64_t*)(b + o_hs); e->d_tokens = (int64_t*)(b + o_tokens);
+    e->d_seq_out = (int64_t*)(b + o_seq); e->d_sargs = (SampleArgs*)(b + o_sa);
+  }
+  auto up = [&](void* d, const void* h, size_t n) { return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st); };
+  CK(up(e->d_tok, tok.data(), (size_t)Mtot * 4));
+  CK(up(e->d_img_row, img_row.data(), (size_t)Mtot * 4));
+  CK(up(e->d_row_seq, row_seq.data(), (size_t)Mtot * 4));
+  CK(up(e->d_row_pos, row_pos.data(), (size_t)Mtot * 4));
+  CK(up(e->d_kv_cap, kv_cap.data(), (size_t)R * 4));
+  CK(up(e->d_pos, seqlen.data(), (size_t)R * 4));
+  CK(up(e->d_last_rows, last_rows.data(), (size_t)R * 4));
+  CK(up(e->d_seqlen, seqlen.data(), (size_t)R * 4));
+  CK(up(e->d_q_row0, q_row0.data(), (size_t)R * 4));
+  CK(up(e->d_kv_off, kv_off.data(), (size_t)R * 8));
+  CK(up(e->d_head_stride, head_stride.data(), (size_t)R * 8));
+  CK(cudaMemsetAsync(e->d_counters, 0, (size_t)R * e->heads_l * 4, st));
+  CK(cudaMemsetAsync(e->d_step, 0, 4, st));
+  CK(cudaStreamSynchronize(st));  // host vectors go out of scope
+
+  // ---- layers over the concatenated rows of all streams
+  float* resid = (float*)e->resid.p;
+  LK(e, launch_embed_rows(e->embed, e->d_tok, e->d_img_row, (const float*)e->img_feats.p, resid, Mtot, H, st));
+  __nv_bfloat16* kbase = (__nv_bfloat16*)e->kv.p;
+  for (int l = 0; l < L; ++l) {
+    const LayerW& w = e->lw[l];
+    void* kc = kbase + (size_t)l * kv_total;
+    void* vc = kbase + (size_t)(L + l) * kv_total;
+    LK(e, launch_rmsnorm_bf16(resid, w.ln1, c.rms_eps, e->xn.p, Mtot, H, nullptr, st));
+    RC(do_gemm(e, e->xn.p, w.wqkv, Mtot, 3 * Hl, H, GEMM_OUT_F32, nullptr, nullptr, (float*)e->qkv.p, nullptr, 3 * Hl, st));
+    LK(e, launch_rope_kv_prefill((const float*)e->qkv.p, Mtot, e->heads_l, 128, e->d_row_seq, e->d_row_pos, e->d_kv_off, e->d_kv_cap,
+                                 e->rope_cos, e->rope_sin, e->qb.p, kc, vc, st));
+    PrefillAttnArgs pa{};
+    pa.q = e->qb.p; pa.q_ld = Hl; pa.k = kc; pa.v = vc; pa.k_off = e->d_kv_off; pa.k_head_stride = e->d_head_stride;
+    pa.k_tok_stride = 128; pa.q_row0 = e->d_q_row0; pa.seqlen = e->d_seqlen; pa.out = e->attn.p; pa.out_ld = Hl;
+    pa.nseq = R; pa.heads = e->heads_l; pa.max_seqlen = max_len; pa.causal = 1; pa.head_dim = 128;
+    pa.scale = 0.08838834764831845f;  // 1/sqrt(128)
+    LK(e, launch_prefill_attn(pa, st));
+    if (c.tp_size > 1) {
+      RC(do_gemm(e, e->attn.p, w.wo, Mtot, H, Hl, GEMM_OUT_F32, nullptr, nullptr, (float*)e->tp_tmp.p, nullptr, H, st));
+      RC(tp_allreduce_add(e, (float*)e->tp_tmp.p, resid, (int64_t)Mtot * H, st));
+    } else {
+      RC(do_gemm(e, e->attn.p, w.wo, Mtot, H, Hl, GEMM_OUT_ADD_F32, nullptr, nullptr, resid, nullptr, H, st));
+    }
+    LK(e, launch_rmsnorm_bf16(resid, w.ln2, c.rms_eps, e->xn.p, Mtot, H, nullptr, st));
+    RC(do_gemm(e, e->xn.p, w.wgu, Mtot, 2 * Il, H, GEMM_OUT_SWIGLU, nullptr, nullptr, nullptr, e->hbuf.p, Il, st));
+    if (c.tp_size > 1) {
+      RC(do_gemm(e, e->hbuf.p, w.wdown, Mtot, H, Il, GEMM_OUT_F32, nullptr, nullptr, (float*)e->tp_tmp.p, nullptr, H, st));
+      RC(tp_allreduce_add(e, (float*)e->tp_tmp.p, resid, (int64_t)Mtot * H, st));
+    } else {
+      RC(do_gemm(e, e->hbuf.p, w.wdown, Mtot, H, Il, GEMM_OUT_ADD_F32, nullptr, nullptr, resid, nullptr, H, st));
+    }
+  }
+  // ---- lm_head on the LAST row of each sequence only (the reference computes all rows, llava_llama.py:103, and reads one, vcd_sample.py:119)
+  LK(e, launch_rmsnorm_bf16(resid, e->final_norm, c.rms_eps, e->xn_d, R, H, e->d_last_rows, st));
+  float* lg = c.tp_size > 1 ? (float*)e->logits_tp.p : (float*)e->logits.p;
+  if (R <= 8) {
+    GemvArgs g{};
+    g.w = e->lm_head; g.x_bf16 = e->xn_d; g.R = R; g.N = e->Vl; g.K = H; g.epilogue = GEMV_OUT_F32; g.out_f32 = lg; g.ld_out = e->Vl;
+    LK(e, launch_gemv(g, e->num_sms, false, st));
+  } else {
+    RC(do_gemm(e, e->xn_d, e->lm_head, R, e->Vl, H, GEMM_OUT_F32, nullptr, nullptr, lg, nullptr, e->Vl, st));
+  }
+  if (c.tp_size > 1) RC(tp_gather_logits(e, st));
+  e->prefilled = true;
+  return VDD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ decode step
+// [tp, R, Vl] (all-gather order) -> [R, V]
+__global__ void tp_logits_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int tp, int R, int Vl) {
+  const int64_t n = (int64_t)tp * R * Vl;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % Vl);
+    const int r = (int)((i / Vl) % R);
+    const int k = (int)(i / ((int64_t)Vl * R));
+    dst[(int64_t)r * tp * Vl + (int64_t)k * Vl + v] = src[i];
+  }
+}
+static int tp_gather_logits(vdd_engine* e, cudaStream_t st) {
+  const int tp = e->c.tp_size, R = e->R, Vl = e->Vl;
+  float* tmp = (float*)e->misc.p;  // sized in vdd_prefill (no allocation inside graph capture)
+  int r = g_nccl.AllGather(e->logits_tp.p, tmp, (size_t)R * Vl, 7, e->comm, st);
+  if (r != 0) return fail(VDD_ERR_CUDA, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  e->launches++;
+  tp_logits_transpose_kernel<<<296, 256, 0, st>>>(tmp, (float*)e->logits.p, tp, R, Vl);
+  e->launches++;
+  CK(cudaGetLastError());
+  return VDD_OK;
+}
+
+static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_t st) {
+  const vdd_config& c = e->c;
+  const int H = c.hidden_size, L = c.num_layers, Hl = e->Hl, Il = e->Il, R = e->R;
+  const bool pdl = e->use_pdl;
+  const bool tp = c.tp_size > 1;
+  LK(e, launch_decode_embed(e->embed, tokens, e->resid_d, e->B, e->S, H, st));
+  __nv_bfloat16* kbase = (__nv_bfloat16*)e->kv.p;
+  for (int l = 0; l < L; ++l) {
+    const LayerW& w = e->lw[l];
+    if (R <= 8) {
+      GemvArgs g{};
+      g.w = w.wqkv; g.x_resid = e->resid_d; g.norm_w = w.ln1; g.eps = c.rms_eps; g.R = R; g.N = 3 * Hl; g.K = H;
+      g.epilogue = GEMV_OUT_F32; g.out_f32 = e->qkv_d; g.ld_out = 3 * Hl;
+      LK(e, launch_gemv(g, e->num_sms, pdl, st));
+    } else {
+      LK(e, launch_rmsnorm_bf16(e->resid_d, w.ln1, c.rms_eps, e->xn_d, R, H, nullptr, st));
+      RC(do_gemm(e, e->xn_d, w.wqkv, R, 3 * Hl, H, GEMM_OUT_F32, nullptr, nullptr, e->qkv_d, nullptr, 3 * Hl, st));
+    }
+    DecodeAttnArgs da{};
+    da.qkv = e->qkv_d; da.kcache = kbase + (size_t)l * e->kv_layer_stride; da.vcache = kbase + (size_t)(L + l) * e->kv_layer_stride;
+    da.kv_off = e->d_kv_off; da.kv_cap = e->d_kv_cap; da.pos = e->d_pos; da.rope_cos = e->rope_cos; da.rope_sin = e->rope_sin;
+    da.out_bf16 = e->attn_d; da.part_o = e->part_o; da.part_ml = e->part_ml; da.counters = e->d_counters;
+    da.R = R; da.heads = e->heads_l; da.max_splits = e->max_splits; da.scale = 0.08838834764831845f;
+    LK(e, launch_decode_attn(da, st));
+    float* o_dst = tp ? (float*)e->tp_tmp.p : e->resid_d;
+    const int o_mode_v = tp ? GEMV_OUT_F32 : GEMV_OUT_ADD_RESID;
+    const int o_mode_m = tp ? GEMM_OUT_F32 : GEMM_OUT_ADD_F32;
+    if (R <= 8) {
+      GemvArgs g{};
+      g.w = w.wo; g.x_bf16 = e->attn_d; g.R = R; g.N = H; g.K = Hl; g.epilogue = o_mode_v; g.out_f32 = o_dst; g.ld_out = H;
+      LK(e, launch_gemv(g, e->num_sms, pdl, st));
+    } else {
+      RC(do_gemm(e, e->attn_d, w.wo, R, H, Hl, o_mode_m, nullptr, nullptr, o_dst, nullptr, H, st));
+    }
+    if (tp) RC(tp_allreduce_add(e, o_dst, e->resid_d, (int64_t)R * H, st));
+    if (R <= 8) {
+      GemvArgs g{};
+      g.w = w.wgu; g.x_resid = e->resid_d; g.norm_w = w.ln2; g.eps = c.rms_eps; g.R = R; g.N = 2 * Il; g.K = H;
+      g.epilogue = GEMV_OUT_SWIGLU_BF16; g.out_bf16 = e->h_d; g.ld_out = Il;
+      LK(e, launch_gemv(g, e->num_sms, pdl, st));
+      GemvArgs d{};
+      d.w = w.wdown; d.x_bf16 = e->h_d; d.R = R; d.N = H; d.K = Il; d.epilogue = o_mode_v; d.out_f32 = o_dst; d.ld_out = H;
+      LK(e, launch_gemv(d, e->num_sms, pdl, st));
+    } else {
+      LK(e, launch_rmsnorm_bf16(e->resid_d, w.ln2, c.rms_eps, e->xn_d, R, H, nullptr, st));
+      RC(do_gemm(e, e->xn_d, w.wgu, R, 2 * Il, H, GEMM_OUT_SWIGLU, nullptr, nullptr, nullptr, e->h_d, Il, st));
+      RC(do_gemm(e, e->h_d, w.wdown, R, H, Il, o_mode_m, nullptr, nullptr, o_dst, nullptr, H, st));
+    }
+    if (tp) RC(tp_allreduce_add(e, o_dst, e->resid_d, (int64_t)R * H, st));
+  }
+  float* lg = tp ? (float*)e->logits_tp.p : (float*)e->logits.p;
+  if (R <= 8) {
+    GemvArgs g{};
+    g.w = e->lm_head; g.x_resid = e->resid_d; g.norm_w = e->final_norm; g.eps = c.rms_eps; g.R = R; g.N = e->Vl; g.K = H;
+    g.epilogue = GEMV_OUT_F32; g.out_f32 = lg; g.ld_out = e->Vl;
+    LK(e, launch_gemv(g, e->num_sms, pdl, st));
+  } else {
+    LK(e, launch_rmsnorm_bf16(e->resid_d, e->final_norm, c.rms_eps, e->xn_d, R, H, nullptr, st));
+    RC(do_gemm(e, e->xn_d, e->lm_head, R, e->Vl, H, GEMM_OUT_F32, nullptr, nullptr, lg, nullptr, e->Vl, st));
+  }
+  if (tp) RC(tp_gather_logits(e, st));
+  return VDD_OK;
+}
+
+extern "C" int vdd_decode_step(vdd_engine* e, const int64_t* tokens, void* stream_v) {
+  if (!e || !tokens) return fail(VDD_ERR_ARG, "null argument");
+  if (!e->prefilled) return fail(VDD_ERR_STATE, "vdd_prefill must run first");
+  cudaStream_t st = (cudaStream_t)stream_v;
+  RC(decode_step_enqueue(e, tokens, st));
+  LK(e, launch_advance(e->d_pos, e->R, nullptr, st));  // pos += 1
+  return VDD_OK;
+}
+extern "C" float* vdd_logits(vdd_engine* e) { return e ? (float*)e->logits.p : nullptr; }
+extern "C" int vdd_num_streams(vdd_engine* e) { return e ? e->S : 0; }
+
+// ------------------------------------------------------------------------------------------------ K8 stand-alone
+static void fill_sample_args(SampleArgs& a, const vdd_sample_params& p) {
+  a.one_plus_alpha = (float)(1.0 + (double)p.cd_alpha);
+  a.alpha = p.cd_alpha;
+  a.log_beta = p.log_cd_beta;
+  a.temperature = p.temperature;
+  a.top_p = p.top_p;
+  a.top_k = p.top_k;
+  a.use_contrast = p.use_contrast;
+  a.eos = p.eos_token_id;
+  a.pad = p.pad_token_id;
+}
+
+extern "C" int vdd_logit_combine_sample(const float* l, const float* u, const float* d, int B, int V, int64_t ld,
+                                        const vdd_sample_params* p, const float* q, float* scores_out, int64_t* tokens_out,
+                                        int32_t* unfinished, void* stream_v) {
+  if (!l || !p || B <= 0 || V <= 0) return fail(VDD_ERR_ARG, "bad argument");
+  if (V > 32768) return fail(VDD_ERR_UNSUPPORTED, "vocab %d > 32768", V);
+  if (!(p->temperature > 0.f)) return fail(VDD_ERR_ARG, "temperature must be > 0");
+  SampleArgs a{};
+  a.l = l; a.u = u; a.d = d; a.q = q; a.scores_out = scores_out; a.tokens_out = tokens_out; a.unfinished = unfinished;
+  a.ld = ld; a.B = B; a.V = V;
+  fill_sample_args(a, *p);
+  cudaError_t ce = launch_combine_sample(a, nullptr, B, V, (cudaStream_t)stream_v);
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "combine_sample: %s", cudaGetErrorString(ce));
+  return VDD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ generate
+extern "C" int vdd_generate(vdd_engine* e, const int64_t* ids, int B, int T, const void* pixels_host, int use_unk, int use_none,
+                            const vdd_sample_params* p, int max_new, const float* q_exp, float* scores_out,
+                            int64_t* tokens_out_host, int* steps_out, void* stream_v) {
+  if (!e || !ids || !p || !tokens_out_host || max_new < 1) return fail(VDD_ERR_ARG, "bad argument");
+  if (e->c.vocab_size > 32768) return fail(VDD_ERR_UNSUPPORTED, "vocab > 32768");
+  if (!(p->temperature > 0.f)) return fail(VDD_ERR_ARG, "temperature must be > 0");
+  cudaStream_t st = (cudaStream_t)stream_v;
+  const vdd_config& c = e->c;
+  CK(cudaEventRecord(e->ev[0], st));
+  if (pixels_host) {
+    const size_t nb = (size_t)B * 3 * c.image_size * c.image_size * 2;
+    RC(ensure(e, e->pix, nb));
+    CK(cudaMemcpyAsync(e->pix.p, pixels_host, nb, cudaMemcpyHostToDevice, st));
+    RC(vdd_encode_images(e, e->pix.p, B, st));
+  }
+  CK(cudaEventRecord(e->ev[1], st));
+  RC(vdd_prefill(e, ids, B, T, pixels_host != nullptr, use_unk, use_none, max_new, st));
+  const int V = c.vocab_size, S = e->S;
+  // device-resident sampler arguments: the graph reads them through a pointer, so one graph serves every call
+  SampleArgs a{};
+  float* lg = (float*)e->logits.p;
+  a.l = lg;
+  int si = 1;
+  a.u = use_unk ? lg + (size_t)(si++) * B * V : nullptr;
+  a.d = use_none ? lg + (size_t)(si++) * B * V : nullptr;
+  a.q = q_exp; a.scores_out = scores_out; a.tokens_out = e->d_tokens; a.seq_out = e->d_seq_out; a.seq_ld = max_new;
+  a.unfinished = e->d_unfinished; a.step_ptr = e->d_step; a.ld = V; a.B = B; a.V = V;
+  fill_sample_args(a, *p);
+  a.use_contrast = (p->use_contrast && S > 1) ? 1 : 0;
+  if (e->pinned_bytes < sizeof(SampleArgs) + (size_t)B * 4 + 64) {
+    if (e->pinned) cudaFreeHost(e->pinned);
+    e->pinned_bytes = sizeof(SampleArgs) + (size_t)B * 4 + 4096;
+    CK(cudaMallocHost(&e->pinned, e->pinned_bytes));
+  }
+  memcpy(e->pinned, &a, sizeof a);
+  int32_t* h_unf = (int32_t*)((char*)e->pinned + align_up(sizeof(SampleArgs), 64));
+  for (int b = 0; b < B; ++b) h_unf[b] = 1;
+  CK(cudaMemcpyAsync(e->d_sargs, e->pinned, sizeof a, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->d_unfinished, h_unf, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  LK(e, launch_combine_sample(a, e->d_sargs, B, V, st));  // step 0 on the prefill logits
+  LK(e, launch_advance(nullptr, 0, e->d_step, st));  // step = 1
+  CK(cudaEventRecord(e->ev[2], st));
+
+  int steps = 1;
+  if (max_new > 1) {
+    const uint64_t key = ((uint64_t)B << 40) ^ ((uint64_t)S << 32) ^ ((uint64_t)e->max_splits << 16) ^ (uint64_t)(e->use_pdl ? 1 : 0) ^
+                         ((uint64_t)(uintptr_t)e->kv.p << 1) ^ (uint64_t)(uintptr_t)e->logits.p ^ ((uint64_t)e->kv_layer_stride << 3);
+    int per_step_launches = 0;
+    const bool graph = e->use_graph && st != nullptr;  // the legacy default stream cannot be captured
+    if (graph && (!e->graph_exec || e->graph_key != key)) {
+      if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+      cudaGraph_t g = nullptr;
+      const int64_t before = e->launches;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int rc = decode_step_enqueue(e, e->d_tokens, st);
+      if (rc == VDD_OK) {
+        cudaError_t ce = launch_combine_sample(a, e->d_sargs, B, V, st);
+        e->launches++;
+        if (ce == cudaSuccess) ce = launch_advance(e->d_pos, e->R, e->d_step, st);
+        e->launches++;
+        if (ce != cudaSuccess) rc = fail(VDD_ERR_CUDA, "capture: %s", cudaGetErrorString(ce));
+      }
+      cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (rc != VDD_OK) { if (g) cudaGraphDestroy(g); return rc; }
+      if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+      e->graph_nodes = (int)(e->launches - before);
+      e->launches = before;
+      ce = cudaGraphInstantiate(&e->graph_exec, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) { e->graph_exec = nullptr; return fail(VDD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+      e->graph_key = key;
+    }
+    per_step_launches = e->graph_nodes;
+    for (int i = 1; i < max_new; ++i) {
+      if (graph) {
+        CK(cudaGraphLaunch(e->graph_exec, st));
+        e->launches += per_step_launches;
+      } else {
+        RC(decode_step_enqueue(e, e->d_tokens, st));
+        LK(e, launch_combine_sample(a, e->d_sargs, B, V, st));
+        LK(e, launch_advance(e->d_pos, e->R, e->d_step, st));
+      }
+      steps = i + 1;
+      // all rows finished? (vcd_sample.py:291: one host sync per step there; here every 16 steps)
+      if (p->eos_token_id >= 0 && (i % 16) == 15 && i + 1 < max_new) {
+        CK(cudaMemcpyAsync(h_unf, e->d_unfinished, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        int any = 0;
+        for (int b = 0; b < B; ++b) any |= h_unf[b];
+        if (!any) break;
+      }
+    }
+  }
+  CK(cudaEventRecord(e->ev[3], st));
+  CK(cudaMemcpy2DAsync(tokens_out_host, (size_t)max_new * 8, e->d_seq_out, (size_t)max_new * 8, (size_t)steps * 8, B,
+                       cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  // trim to the step at which the reference would have left its loop (all rows finished)
+  if (p->eos_token_id >= 0) {
+    std::vector<int> unf(B, 1);
+    for (int i = 0; i < steps; ++i) {
+      int any = 0;
+      for (int b = 0; b < B; ++b) {
+        if (unf[b] && tokens_out_host[(size_t)b * max_new + i] == p->eos_token_id) unf[b] = 0;
+        any |= unf[b];
+      }
+      if (!any) { steps = i + 1; break; }
+    }
+  }
+  if (steps_out) *steps_out = steps;
+  cudaEventElapsedTime(&e->t_vision, e->ev[0], e->ev[1]);
+  cudaEventElapsedTime(&e->t_prefill, e->ev[1], e->ev[2]);
+  cudaEventElapsedTime(&e->t_decode, e->ev[2], e->ev[3]);
+  return VDD_OK;
+}
+
+extern "C" int64_t vdd_launch_count(vdd_engine* e, int reset) {
+  if (!e) return 0;
+  const int64_t n = e->launches;
+  if (reset) e->launches = 0;
+  return n;
+}
+extern "C" int vdd_last_timings(vdd_engine* e, float* v, float* p, float* d) {
+  if (!e) return VDD_ERR_ARG;
+  if (v) *v = e->t_vision;
+  if (p) *p = e->t_prefill;
+  if (d) *d = e->t_decode;
+  return VDD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ TP
+extern "C" int vdd_tp_unique_id(void* id128) {
+  if (!nccl_load()) return fail(VDD_ERR_UNSUPPORTED, "libnccl.so.2 not loadable (set VDD_NCCL_LIB): %s", dlerror());
+  int r = g_nccl.GetUniqueId(id128);
+  if (r != 0) return fail(VDD_ERR_CUDA, "ncclGetUniqueId failed (%d)", r);
+  return VDD_OK;
+}
+extern "C" int vdd_tp_init(vdd_engine* e, const void* id128) {
+  if (!e || !id128) return fail(VDD_ERR_ARG, "null argument");
+  if (e->c.tp_size <= 1) return VDD_OK;
+  if (!nccl_load()) return fail(VDD_ERR_UNSUPPORTED, "libnccl.so.2 not loadable (set VDD_NCCL_LIB): %s", dlerror());
+  NcclId nid;
+  memcpy(nid.b, id128, 128);
+  int r = g_nccl.CommInitRank(&e->comm, e->c.tp_size, nid, e->c.tp_rank);
+  if (r != 0) return fail(VDD_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return VDD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stand-alone kernel entries
+extern "C" int vdd_gemv(const void* w, const void* x_bf16, const float* x_resid, const void* norm_w, float eps, int R, int N,
+                        int K, int epilogue, float* out_f32, void* out_bf16, void* stream_v) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  GemvArgs g{};
+  g.w = w; g.x_bf16 = x_bf16; g.x_resid = x_resid; g.norm_w = norm_w; g.eps = eps; g.R = R; g.N = N; g.K = K;
+  g.epilogue = epilogue; g.out_f32 = out_f32; g.out_bf16 = out_bf16;
+  g.ld_out = epilogue == GEMV_OUT_SWIGLU_BF16 ? N / 2 : N;
+  cudaError_t ce = launch_gemv(g, sms, getenv("VDD_NO_PDL") == nullptr, (cudaStream_t)stream_v);
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "gemv R=%d N=%d K=%d: %s", R, N, K, cudaGetErrorString(ce));
+  return VDD_OK;
+}
+extern "C" int vdd_gemm(const void* a, const void* w, int M, int N, int K, int epilogue, const void* bias, const int32_t* row_map,
+                        float* out_f32, void* out_bf16, int64_t ldc, void* stream_v) {
+  GemmArgs g{a, w, M, N, K, epilogue, bias, row_map, out_f32, out_bf16, ldc};
+  cudaError_t ce = launch_gemm(g, (cudaStream_t)stream_v);
+  if (ce != cudaSuccess)
+    return fail(VDD_ERR_CUDA, "gemm M=%d N=%d K=%d: %s %s", M, N, K, cudaGetErrorString(ce), gemm_init_error() ? gemm_init_error() : "");
+  return VDD_OK;
+}

@@ -1,0 +1,226 @@
+// Tensor-core GEMM for the GEMM-shaped parts of the VDD path (LLM prefill of all streams, CLIP ViT, mm_projector,
+// and decode steps with more than 8 fused rows):   C[M, N] = A[M, K] . W[N, K]^T   (bf16 in, fp32 accumulate).
+//
+// Replaces the cuBLAS fp16 GEMMs behind HF LlamaModel / CLIPVisionModel / the projector MLP that the reference
+// triggers from llava_llama.py:91-103, clip_encoder.py:48 and llava_arch.py:84.
+//
+// sm_100a design: one 128x128 output tile per CTA; operands arrive by TMA (cp.async.bulk.tensor, 128B swizzle,
+// out-of-bounds rows/columns zero-filled so M, N, K need not be tile multiples) into a 4-stage shared-memory ring
+// guarded by full/empty mbarriers; ONE thread issues tcgen05.mma (UMMA 128x128x16, kind::f16, bf16 inputs) with the
+// fp32 accumulator in 128 TMEM columns; tcgen05.commit releases ring slots and finally signals the epilogue warps,
+// which read TMEM with tcgen05.ld (32 lanes x 16 columns) and apply the fused epilogue (bias, quick_gelu / gelu,
+// residual add, SwiGLU over interleaved gate/up columns, row remap for the image splice) straight to global memory.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (one TMEM lane quadrant each).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vdd {
+
+constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 64, GM_STAGES = 4;
+constexpr int GM_THREADS = 192;
+constexpr int GM_STAGE_BYTES = (GM_BM + GM_BN) * GM_BK * 2;  // 32 KB
+constexpr int GM_SMEM = GM_STAGES * GM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmEpi {
+  int M, N, K, mode;
+  const __nv_bfloat16* bias;
+  const int32_t* row_map;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  int64_t ldc;
+};
+
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + expf(-1.702f * x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmEpi ep) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GM_STAGES * GM_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + GM_STAGES;
+  uint64_t* tmem_full = empty_bar + GM_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * GM_BN, m0 = blockIdx.y * GM_BM;
+  const int nkb = (ep.K + GM_BK - 1) / GM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < GM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<GM_BN>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % GM_STAGES;
+        mbar_wait(&empty_bar[s], ((kb / GM_STAGES) & 1) ^ 1);
+        unsigned char* sa = smem + s * GM_STAGE_BYTES;
+        unsigned char* sb = sa + GM_BM * GM_BK * 2;
+        mbar_arrive_expect_tx(&full_bar[s], GM_STAGE_BYTES);
+        tma_load_2d(sa, &tmap_a, &full_bar[s], kb * GM_BK, m0);
+        tma_load_2d(sb, &tmap_b, &full_bar[s], kb * GM_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (single thread)
+      constexpr uint32_t idesc = umma_idesc_bf16(GM_BM, GM_BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % GM_STAGES;
+        mbar_wait(&full_bar[s], (kb / GM_STAGES) & 1);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + s * GM_STAGE_BYTES);
+        const uint32_t sb = sa + GM_BM * GM_BK * 2;
+        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < GM_BK / 16; ++k)
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);  // +32 B along K
+        umma_commit(&empty_bar[s]);  // frees the ring slot once these MMAs have read it
+      }
+      umma_commit(tmem_full);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31  (rows of the tile)
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    int64_t orow = -1;
+    if (row < ep.M) orow = ep.row_map ? ep.row_map[row] : row;
+#pragma unroll 1
+    for (int c = 0; c < GM_BN / 16; ++c) {
+      uint32_t rr[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + c * 16, rr);
+      tmem_ld_wait();
+      const int col = n0 + c * 16;
+      if (orow >= 0 && col < ep.N) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
+      if (ep.bias) {
+        const uint4 b0 = *reinterpret_cast<const uint4*>(ep.bias + col);
+        const uint4 b1 = *reinterpret_cast<const uint4*>(ep.bias + col + 8);
+        const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[2 * i] += bf16lo(bw[i]); v[2 * i + 1] += bf16hi(bw[i]); }
+      }
+      if (ep.mode == GEMM_OUT_F32 || ep.mode == GEMM_OUT_ADD_F32) {
+        float4* o = reinterpret_cast<float4*>(ep.out_f32 + orow * ep.ldc + col);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 t = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          if (ep.mode == GEMM_OUT_ADD_F32) {
+            const float4 old = o[i];
+            t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+          }
+          o[i] = t;
+        }
+      } else if (ep.mode == GEMM_OUT_SWIGLU) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float g0 = v[4 * i], u0 = v[4 * i + 1], g1 = v[4 * i + 2], u1 = v[4 * i + 3];
+          pk[i] = pack_bf16(g0 / (1.0f + expf(-g0)) * u0, g1 / (1.0f + expf(-g1)) * u1);
+        }
+        *reinterpret_cast<uint4*>(ep.out_bf16 + orow * ep.ldc + (col >> 1)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      } else {
+        if (ep.mode == GEMM_OUT_BF16_QGELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = quick_gelu(v[i]);
+        } else if (ep.mode == GEMM_OUT_BF16_GELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+        uint4* o = reinterpret_cast<uint4*>(ep.out_bf16 + orow * ep.ldc + col);
+        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      }
+      __syncwarp();
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<GM_BN>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static const char* g_init_err = nullptr;
+
+static bool gemm_init() {
+  static bool done = false;
+  if (done) return g_encode != nullptr;
+  done = true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    g_init_err = "cuTensorMapEncodeTiled not available from the driver";
+    return false;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
+  if (e != cudaSuccess) {
+    g_init_err = "cudaFuncSetAttribute(gemm_tc_kernel) failed";
+    g_encode = nullptr;
+    return false;
+  }
+  return true;
+}
+const char* gemm_init_error() { return g_init_err; }
+
+// 2D bf16 row-major [rows, K] tensor map with a {64, 128} box and 128-byte swizzle
+static bool make_tmap(CUtensorMap* m, const void* ptr, int rows, int K) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {GM_BK, GM_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+  if (!gemm_init()) return cudaErrorNotSupported;
+  if (a.M <= 0) return cudaSuccess;
+  if ((a.K % 8) != 0 || (a.N % 16) != 0 || ((uintptr_t)a.a & 15) || ((uintptr_t)a.w & 15)) return cudaErrorInvalidValue;
+  CUtensorMap ta, tb;
+  if (!make_tmap(&ta, a.a, a.M, a.K) || !make_tmap(&tb, a.w, a.N, a.K)) return cudaErrorInvalidValue;
+  GemmEpi ep;
+  ep.M = a.M; ep.N = a.N; ep.K = a.K; ep.mode = a.epilogue;
+  ep.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
+  ep.row_map = a.row_map;
+  ep.out_f32 = a.out_f32;
+  ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+  ep.ldc = a.ldc;
+  dim3 grid((a.N + GM_BN - 1) / GM_BN, (a.M + GM_BM - 1) / GM_BM);
+  gemm_tc_kernel<<<grid, GM_THREADS, GM_SMEM, stream>>>(ta, tb, ep);
+  return cudaGetLastError();
+}
+
+}  // namespace vdd

@@ -1,0 +1,121 @@
+// Host-visible launch wrappers of the VDD kernels (internal to libvdd; the public surface is include/vdd.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vdd {
+
+// ---------------------------------------------------------------- K8 combine + sample
+struct SampleArgs {
+  const float *l, *u, *d;  // [B, V] with row pitch ld
+  const float* q;          // [steps, B, V] Exp(1) variates or null
+  float* scores_out;       // [steps, B, V] or null
+  int64_t* tokens_out;     // [B] or null
+  int64_t* seq_out;        // [B, seq_ld]: column `step` receives the token, or null
+  int32_t* unfinished;     // [B] or null
+  const int32_t* step_ptr; // device step counter (graph replay) or null => step 0
+  int64_t ld, seq_ld, eos, pad;
+  int B, V, top_k, use_contrast;
+  float one_plus_alpha, alpha, log_beta, temperature, top_p;
+};
+cudaError_t launch_combine_sample(const SampleArgs& args, const SampleArgs* dptr, int B, int V, cudaStream_t stream);
+
+// ---------------------------------------------------------------- decode GEMV (R <= 8 rows of x against W[N,K])
+enum GemvPrologue { GEMV_X_BF16 = 0, GEMV_X_RMSNORM = 1 };
+enum GemvEpilogue { GEMV_OUT_F32 = 0, GEMV_OUT_ADD_RESID = 1, GEMV_OUT_SWIGLU_BF16 = 2 };
+struct GemvArgs {
+  const void* w;        // bf16 [N, K] row-major
+  const void* x_bf16;   // bf16 [R, K] (GEMV_X_BF16)
+  const float* x_resid; // fp32 [R, K] residual stream (GEMV_X_RMSNORM)
+  const void* norm_w;   // bf16 [K]
+  float eps;
+  int R, N, K;
+  int epilogue;
+  float* out_f32;       // [R, N] (OUT_F32: store; ADD_RESID: +=)
+  void* out_bf16;       // [R, N/2] (SWIGLU)
+  int64_t ld_out;       // row pitch of the output in elements
+};
+cudaError_t launch_gemv(const GemvArgs& a, int num_sms, bool pdl, cudaStream_t stream);
+
+// ---------------------------------------------------------------- tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T
+enum GemmEpilogue {
+  GEMM_OUT_F32 = 0,        // out_f32[row, col] = acc (+bias)
+  GEMM_OUT_ADD_F32 = 1,    // out_f32[row, col] += acc (+bias)
+  GEMM_OUT_BF16 = 2,       // out_bf16 = acc (+bias)
+  GEMM_OUT_BF16_QGELU = 3, // quick_gelu(acc+bias)   (CLIP MLP)
+  GEMM_OUT_BF16_GELU = 4,  // gelu_erf(acc+bias)     (mm_projector)
+  GEMM_OUT_SWIGLU = 5      // out_bf16[row, col/2] = silu(acc[2i]) * acc[2i+1]  (interleaved gate/up)
+};
+struct GemmArgs {
+  const void* a;  // bf16 [M, K] row-major (lda = K)
+  const void* w;  // bf16 [N, K] row-major
+  int M, N, K;
+  int epilogue;
+  const void* bias;        // bf16 [N] or null
+  const int32_t* row_map;  // out row = row_map[row] (or row when null); <0 skips the row
+  float* out_f32;
+  void* out_bf16;
+  int64_t ldc;
+};
+cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
+const char* gemm_init_error();
+
+// ---------------------------------------------------------------- attention
+struct DecodeAttnArgs {
+  const float* qkv;     // fp32 [R, 3*Hl] (q | k | v) of the new token, pre-RoPE
+  void* kcache;         // bf16, this layer: row r, head h at kcache + kv_off[r] + h*cap[r]*D
+  void* vcache;
+  const int64_t* kv_off;   // [R] element offset of the row's block inside the layer
+  const int32_t* kv_cap;   // [R] capacity (tokens) of the row
+  const int32_t* pos;      // [R] position of the new token = number of cached tokens
+  const float* rope_cos;   // [max_pos, D/2]
+  const float* rope_sin;
+  void* out_bf16;       // [R, Hl]
+  float* part_o;        // workspace [R*heads*max_splits, D]
+  float* part_ml;       // workspace [R*heads*max_splits, 2]
+  int32_t* counters;    // [R*heads] zero on entry, zero on exit
+  int R, heads, max_splits;
+  float scale;
+};
+cudaError_t launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t stream);
+
+struct PrefillAttnArgs {
+  const void* q;  // bf16; query i of sequence s, head h at q + (q_row0[s] + i)*q_ld + h*D
+  int64_t q_ld;
+  const void* k;  // bf16; key t of (s, h) at k + k_off[s] + h*k_head_stride[s] + t*k_tok_stride
+  const void* v;
+  const int64_t* k_off;          // [nseq]
+  const int64_t* k_head_stride;  // [nseq]
+  int64_t k_tok_stride;
+  const int32_t* q_row0;  // [nseq]
+  const int32_t* seqlen;  // [nseq]
+  void* out;              // bf16, same addressing as q with out_ld
+  int64_t out_ld;
+  int nseq, heads, max_seqlen, causal, head_dim;
+  float scale;
+};
+cudaError_t launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t stream);
+
+// ---------------------------------------------------------------- element-wise / glue
+cudaError_t launch_rmsnorm_bf16(const float* x, const void* w_bf16, float eps, void* out_bf16, int rows, int H,
+                                const int32_t* row_idx, cudaStream_t stream);
+cudaError_t launch_layernorm(const float* x, const void* w_bf16, const void* b_bf16, float eps, void* out_bf16,
+                             float* out_f32, int rows, int H, const int32_t* row_idx, cudaStream_t stream);
+cudaError_t launch_embed_rows(const void* table_bf16, const int32_t* tok, const int32_t* img_row,
+                              const float* img_feats, float* resid, int rows, int H, cudaStream_t stream);
+cudaError_t launch_rope_kv_prefill(const float* qkv, int rows, int heads, int D, const int32_t* row_seq,
+                                   const int32_t* row_pos, const int64_t* kv_off, const int32_t* kv_cap,
+                                   const float* rope_cos, const float* rope_sin, void* q_out_bf16, void* kcache,
+                                   void* vcache, cudaStream_t stream);
+cudaError_t launch_rope_table(float* cos_t, float* sin_t, int max_pos, int D, float theta, cudaStream_t stream);
+cudaError_t launch_im2col(const void* pixels_bf16, void* out_bf16, int B, int S, int P, int Kpad, cudaStream_t stream);
+cudaError_t launch_vit_embed(const float* patch_out, const void* cls_bf16, const void* pos_bf16, float* resid, int B,
+                             int NP, int H, cudaStream_t stream);
+cudaError_t launch_decode_embed(const void* table_bf16, const int64_t* tokens, float* resid, int B, int S, int H,
+                                cudaStream_t stream);
+cudaError_t launch_advance(int32_t* pos, int R, int32_t* step, cudaStream_t stream);  // pos[r] += 1, *step += 1
+cudaError_t launch_add_rows(float* dst, const float* src, int64_t n, cudaStream_t stream);
+cudaError_t launch_cast_rows_bf16(const float* src, void* dst_bf16, int rows, int H, const int32_t* row_idx,
+                                  cudaStream_t stream);
+
+}  // namespace vdd

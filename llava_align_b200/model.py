@@ -1,0 +1,160 @@
+"""The reference's model-level surface, backed by libvdd.
+
+`LlavaLlamaForCausalLM.generate(input_ids, images=..., use_dd=..., use_dd_unk=..., cd_alpha=..., cd_beta=..., ...)`
+keeps the argument names, defaults and return layouts the reference's drivers rely on
+(reference experiments/eval/sampling/llava_sampling.py:96-109, eval/calibrate/llava_calibrate.py:160-185):
+
+  * VDD is active only after `evolve_vcd_sampling()` (vcd_utils/vcd_sample.py:325-326) and only when
+    `do_sample=True` (do_sample=False dispatches to HF greedy_search, which the reference does not patch);
+  * it is switched on by `use_dd`, `use_dd_unk` (vcd_sample.py:122-124,147); `cd_alpha` defaults to 0.5 and
+    `cd_beta` to 0.1 when None (vcd_sample.py:188-189);
+  * warpers follow HF-4.31 `_get_logits_warper`: a kwarg that is passed (even as None) overrides
+    `generation_config`, Temperature -> TopK -> TopP;
+  * the result starts with the untouched input_ids, -200 sentinel included (llava_sampling.py:111-114).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import engine as _engine
+from .config import VddConfig, IMAGE_TOKEN_INDEX
+
+_VDD_SAMPLER_INSTALLED = False
+
+
+def evolve_vcd_sampling():
+    """Install the VDD sampler (reference vcd_utils/vcd_sample.py:325-326).  Zero-arg, idempotent."""
+    global _VDD_SAMPLER_INSTALLED
+    _VDD_SAMPLER_INSTALLED = True
+
+
+def vdd_sampler_installed() -> bool:
+    return _VDD_SAMPLER_INSTALLED
+
+
+class GenerateOutput(dict):
+    """Mapping with attribute access, like HF's SampleDecoderOnlyOutput (vcd_sample.py:316-321)."""
+    __getattr__ = dict.get
+
+
+class _VisionTowerHandle:
+    """What drivers touch on `model.get_vision_tower()` (llava_sampling.py:49-53)."""
+
+    def __init__(self, image_processor=None):
+        self.is_loaded = True
+        self.image_processor = image_processor
+
+    def load_model(self):
+        self.is_loaded = True
+
+    def to(self, *a, **k):
+        return self
+
+
+class LlavaLlamaForCausalLM:
+    def __init__(self, cfg: VddConfig, device="cuda:0", tp_size=1, tp_rank=0, image_processor=None):
+        self.vdd_config = cfg
+        self.engine = _engine.VddEngine(cfg, device, tp_size, tp_rank)
+        self.device = self.engine.device
+        self.dtype = torch.bfloat16
+        self.config = SimpleNamespace(mm_use_im_start_end=False, mm_use_im_patch_token=False, vocab_size=cfg.vocab_size,
+                                      hidden_size=cfg.hidden_size, pad_token_id=cfg.pad_token_id,
+                                      eos_token_id=cfg.eos_token_id, bos_token_id=cfg.bos_token_id,
+                                      max_sequence_length=cfg.max_position_embeddings, is_encoder_decoder=False)
+        # HF GenerationConfig defaults (temperature 1.0, top_k 50, top_p 1.0)
+        self.generation_config = SimpleNamespace(temperature=1.0, top_k=50, top_p=1.0, do_sample=False, max_new_tokens=None,
+                                                 max_length=20, eos_token_id=cfg.eos_token_id, pad_token_id=cfg.pad_token_id,
+                                                 output_scores=False, output_attentions=False, return_dict_in_generate=False)
+        self._vt = _VisionTowerHandle(image_processor)
+
+    # ---- driver-facing odds and ends
+    def get_vision_tower(self):
+        return self._vt
+
+    def resize_token_embeddings(self, n):
+        if n != self.vdd_config.vocab_size:
+            raise NotImplementedError("resizing the vocabulary of a loaded engine is not supported")
+
+    def eval(self):
+        return self
+
+    def cuda(self, *a, **k):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def load_state_dict(self, sd, strict=True):
+        self.engine.load_state_dict(sd)
+
+    # ---- generate
+    @torch.no_grad()
+    def generate(self, input_ids=None, images=None, images_cd=None, cd_alpha=None, cd_beta=None, use_dd=None,
+                 use_dd_unk=None, max_new_tokens=None, max_length=None, use_cache=True, num_beams=1, stopping_criteria=None,
+                 attention_mask=None, **kwargs):
+        if input_ids is None:
+            input_ids = kwargs.pop("inputs")
+        gc = self.generation_config
+        opt = {k: kwargs.pop(k) if k in kwargs else getattr(gc, k) for k in
+               ("do_sample", "temperature", "top_k", "top_p", "output_scores", "output_attentions",
+                "return_dict_in_generate", "eos_token_id", "pad_token_id")}
+        kwargs.pop("output_hidden_states", None)
+        if kwargs:
+            raise ValueError(f"The following `model_kwargs` are not used by the model: {sorted(kwargs)}")  # HF _validate_model_kwargs
+        if num_beams != 1:
+            raise NotImplementedError("beam search is outside the VDD path (reference scripts use num_beams=1)")
+        if images_cd is not None:
+            raise NotImplementedError("use_cd (VCD noise stream, images_cd) is a 'next' row of the scope table, not built yet")
+        if input_ids.dim() == 1:
+            input_ids = input_ids.unsqueeze(0)
+        B, T = input_ids.shape
+        if max_new_tokens is None:
+            max_new_tokens = gc.max_new_tokens
+        if max_new_tokens is None:
+            max_new_tokens = (max_length or gc.max_length) - T
+        if max_new_tokens < 1:
+            raise ValueError("max_new_tokens must be >= 1")
+        eos = opt["eos_token_id"]
+        if isinstance(eos, (list, tuple)):
+            if len(eos) > 1:
+                raise NotImplementedError("a single eos_token_id is supported")
+            eos = eos[0] if eos else None
+        pad = opt["pad_token_id"]
+        if eos is not None and pad is None:
+            raise ValueError("If `eos_token_id` is defined, make sure that `pad_token_id` is defined.")  # vcd_sample.py:258-259
+
+        has_image = images is not None and bool((input_ids == IMAGE_TOKEN_INDEX).any())
+        do_sample = bool(opt["do_sample"])
+        vdd = do_sample and vdd_sampler_installed() and bool(use_dd or use_dd_unk)
+        use_unk = bool(vdd and use_dd_unk)
+        use_none = bool(vdd and use_dd)
+        if do_sample:
+            t, k, p = opt["temperature"], opt["top_k"], opt["top_p"]
+            if t is not None and not t > 0:
+                raise ValueError("`temperature` has to be a strictly positive float")
+            params = _engine.make_sample_params(
+                cd_alpha=0.5 if cd_alpha is None else cd_alpha, cd_beta=0.1 if cd_beta is None else cd_beta,
+                temperature=None if (t is None or t == 1.0) else t, top_k=None if (k is None or k == 0) else k,
+                top_p=None if (p is None or p >= 1.0) else p, use_contrast=vdd, eos_token_id=eos, pad_token_id=pad)
+        else:  # greedy_search: argmax of the main stream, no VDD
+            params = _engine.make_sample_params(use_contrast=False, eos_token_id=eos, pad_token_id=pad)
+        V = self.vdd_config.vocab_size
+        q = None
+        if do_sample and params.top_k != 1:
+            # torch.multinomial(probs, 1) == argmax(probs / Exp(1)); the variates come from torch's CUDA generator
+            q = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device).exponential_(1)
+        want_scores = bool(opt["output_scores"] and opt["return_dict_in_generate"])
+        scores_buf = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device) if want_scores else None
+        new_tokens, steps = self.engine.generate(input_ids, images if has_image else None, use_unk, use_none, params,
+                                                 max_new_tokens, q, scores_buf)
+        seq = torch.cat([input_ids.to("cpu", torch.int64), new_tokens], dim=1).to(input_ids.device)
+        if not opt["return_dict_in_generate"]:
+            return seq
+        out = GenerateOutput(sequences=seq)
+        out["scores"] = tuple(scores_buf[i] for i in range(steps)) if want_scores else None
+        out["attentions"] = None  # per-step attention maps are not materialised by the fused kernels (scope table row f-1)
+        out["hidden_states"] = None
+        return out
