@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Headline benchmark: LLaVA-1.5-7B Visual-Debias-Decoding tokens/s (BASELINE.json config 2: bf16, batch 1, one 336px
+image, 32-token prompt, 256 new tokens, use_dd + use_dd_unk => 3 fused streams), random-init weights, synthetic inputs.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (libvdd)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port), bounded sample
+
+One "step" = one whole generate() of the workload.  `value` is measured with inputs resident in HBM, `e2e` through
+model.generate() with pinned HOST inputs (pixels H2D and tokens D2H inside the timed region).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LLaVA-1.5-7B VDD decode tokens/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="llava-v1.5-7b")
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--prompt-len", type=int, default=32)
+    ap.add_argument("--new-tokens", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="under ncu: the device-resident leg only, no extra launches")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.p:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx = float(c[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def synthetic_inputs(cfg, B, T, seed=0):
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(seed)
+    ids = torch.from_numpy(rng.integers(3, cfg.vocab_size, size=(B, T)).astype("int64"))
+    ids[:, 1 + T // 8] = -200  # <image> right after the system preamble (llava_sampling.py:69-79)
+    img = torch.from_numpy(rng.standard_normal((B, 3, cfg.image_size, cfg.image_size), dtype="float32")).to(torch.bfloat16)
+    return ids, img
+
+
+def algorithmic_bytes(cfg, tp=1):
+    """Weights read once per decode step for ALL fused streams."""
+    H, I, V, L = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.num_hidden_layers
+    per_layer = 4 * H * H + 3 * H * I
+    proj = 2 * (L * per_layer + V * H) // tp
+    kv_tok = L * 2 * H * 2 // tp
+    return proj, kv_tok
+
+
+def run_reference(a):
+    """Reference arm: the reference's CPU path (oracle port) on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from llava_align_b200.config import by_name
+    from oracle import cpu_baseline as cb
+    cfg = by_name(a.model)
+    vals, last = [], None
+    for i in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        r = cb.time_reference_path(cfg, B=a.batch, T=a.prompt_len, n_new=3)
+        if i >= a.warmup:
+            vals.append(cb.tokens_per_s(r, a.batch, a.new_tokens))
+            last = r
+        if time.perf_counter() - t0 > 120 and i + 1 >= a.warmup + 1:
+            break
+    v = sum(vals) / len(vals)
+    ms = 1000.0 * a.batch * a.new_tokens / v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": a.gpus, "steps": len(vals),
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(a, cfg, 1),
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": last["cores"], "kind": "port", "sample": last["sample"],
+                             "phases": {k: last[k] for k in ("vision_s", "prefill_s", "decode_s_per_token")}},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, cfg, n):
+    return {"workload": f"BASELINE.json configs[1]: {cfg.name} bf16 random-init, batch {a.batch}, 1 synthetic "
+                        f"{cfg.image_size}px image, {a.prompt_len}-token prompt, {a.new_tokens} new tokens, use_dd+use_dd_unk "
+                        f"(3 fused streams), cd_alpha=1 cd_beta=0.1, temperature-1 sampling, EOS disabled",
+            "global_batch": a.batch, "new_tokens": a.new_tokens, "prompt_len": a.prompt_len, "streams": 3,
+            "parallelism": "single GPU" if n == 1 else f"tp{n} (heads/FFN/vocab split, NCCL all-reduce)",
+            "l2_policy": "inputs larger than L2: every step streams the 13.2 GB of weights (L2 = 126 MB); no flush needed"}
+
+
+def main():
+    a = parse()
+    if a.profile:
+        a.no_e2e = a.no_cpu_baseline = True
+    if a.impl == "reference":
+        return run_reference(a)
+    import torch
+    import torch.distributed as dist
+    from llava_align_b200 import _lib
+    from llava_align_b200 import engine as E
+    from llava_align_b200.builder import load_pretrained_model
+    from llava_align_b200.config import by_name
+    from llava_align_b200.model import evolve_vcd_sampling
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = by_name(a.model)
+    evolve_vcd_sampling()
+    tok, model, _, _ = load_pretrained_model(f"random:{a.model}:0", None, a.model, device=str(dev), tp_size=world, tp_rank=rank)
+    eng = model.engine
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(E.VddEngine.tp_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(idt, 0)
+        eng.tp_init(bytes(idt.cpu().numpy().tobytes()))
+    B, T, n_new = a.batch, a.prompt_len, a.new_tokens
+    ids, img = synthetic_inputs(cfg, B, T)
+    img_pinned = img.pin_memory()
+    img_dev = img.to(dev)
+    ids_pinned = ids.pin_memory()
+    V = cfg.vocab_size
+    params = E.make_sample_params(cd_alpha=1.0, cd_beta=0.1, use_contrast=True, eos_token_id=None)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    q = torch.empty(n_new, B, V, device=dev).exponential_(1, generator=g)  # identical on every TP rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, warm, steps):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.launch_count(reset=True)
+        with torch.cuda.stream(eng.stream):
+            e0.record(eng.stream)
+            for _ in range(steps):
+                fn()
+            e1.record(eng.stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, eng.launch_count()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- value: inputs resident in HBM
+    dev_fn = lambda: eng.generate(ids, img_dev, True, True, params, n_new, q, None)
+    ms, launches = timed(dev_fn, a.warmup, a.steps)
+    tm = eng.last_timings()
+    value = B * n_new * a.steps / (ms / 1e3)
+    # ---- e2e: the reference-facing call with pinned host buffers (H2D pixels, D2H tokens inside)
+    e2e = None
+    if not a.no_e2e:
+        gen_kw = dict(images=img_pinned, images_cd=None, cd_alpha=1.0, cd_beta=0.1, use_dd=True, use_dd_unk=True, do_sample=True,
+                      temperature=1.0, top_p=None, top_k=None, max_new_tokens=n_new, use_cache=True, eos_token_id=None)
+        if world > 1:
+            torch.manual_seed(4321)  # all TP ranks must draw the same variates
+        e2e_fn = lambda: model.generate(ids_pinned, **gen_kw)
+        ms2, _ = timed(e2e_fn, 1, a.steps)
+        e2e = {"value": B * n_new * a.steps / (ms2 / 1e3), "unit": "tokens/s",
+               "h2d_bytes_per_step": int(img.numel() * 2 + ids.numel() * 8), "d2h_bytes_per_step": int(B * n_new * 8),
+               "ms_per_step": ms2 / a.steps}
+    clocks = sampler.stop() if sampler else None
+
+    # ---- roofline of the dominant kernel (gemv_kernel: every projection of the decode step), timed live with CUDA events
+    proj_bytes, kv_tok = algorithmic_bytes(cfg, world)
+    L = cfg.num_hidden_layers
+    n_gemv = 4 * L + 1
+    lib = _lib.load()
+    reps = 1 if a.profile else 20
+    with torch.cuda.stream(eng.stream):
+        for _ in range(0 if a.profile else 3):
+            _lib.check(lib.vdd_bench_projection_chain(eng.h, eng.stream.cuda_stream), "chain")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(eng.stream)
+        for _ in range(reps):
+            _lib.check(lib.vdd_bench_projection_chain(eng.h, eng.stream.cuda_stream), "chain")
+        e1.record(eng.stream)
+    torch.cuda.synchronize()
+    chain_ms = e0.elapsed_time(e1) / reps
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = proj_bytes / (chain_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "gemv_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "vdd::gemv_kernel (decode projections, 3 fused rows)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": proj_bytes / n_gemv, "us_per_launch": 1e3 * chain_ms / n_gemv, "launches_per_step": n_gemv,
+                "how": f"CUDA events around {reps} back-to-back replays of one decode step's {n_gemv} projection launches"}
+    # whole decode step against its own algorithmic bytes (weights once + KV of all rows + logits)
+    ctx_mid = (T + cfg.num_patches - 1) + T + (T - 1) + 3 * (n_new // 2)
+    step_bytes = proj_bytes + B * ctx_mid * kv_tok + 3 * B * V * 4
+    step_ms = tm["decode_ms"] / max(1, n_new - 1)
+    decode = {"ms_per_token_step": step_ms, "tokens_per_s_decode_only": B * 1e3 / step_ms if step_ms > 0 else None,
+              "algorithmic_GB_per_step": step_bytes / 1e9, "achieved_GBps": step_bytes / (step_ms / 1e3) / 1e9 if step_ms > 0 else None,
+              "frac_of_peak": (step_bytes / (step_ms / 1e3) / 1e9 / peak) if step_ms > 0 else None,
+              "vision_ms": tm["vision_ms"], "prefill_ms": tm["prefill_ms"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import cpu_baseline as cb
+        r = cb.time_reference_path(cfg, B=B, T=T, n_new=3)
+        cpu = {"value": cb.tokens_per_s(r, B, n_new), "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "phases": {k: r[k] for k in ("vision_s", "prefill_s", "decode_s_per_token")}}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_config(a, cfg, world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "decode_step": decode, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

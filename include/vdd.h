@@ -118,6 +118,9 @@ VDD_API int vdd_tp_init(vdd_engine* e, const void* id128_host);
 VDD_API int64_t vdd_launch_count(vdd_engine* e, int reset);
 VDD_API int vdd_last_timings(vdd_engine* e, float* vision_ms, float* prefill_ms, float* decode_ms);
 
+/* Enqueue one decode step's projection kernels only (4 per layer + lm_head), for bench.py's roofline leg. */
+VDD_API int vdd_bench_projection_chain(vdd_engine* e, void* stream);
+
 /* Stand-alone kernel entry points used by the unit tests and micro-benchmarks (same kernels the engine runs). */
 VDD_API int vdd_gemv(const void* w_bf16, const void* x_bf16, const float* x_f32_resid, const void* norm_w_bf16, float eps,
              int R, int N, int K, int epilogue, float* out_f32, void* out_bf16, void* stream);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "vdd_tp_init": (C.c_int, [_P, _P]),
     "vdd_launch_count": (C.c_int64, [_P, C.c_int]),
     "vdd_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "vdd_bench_projection_chain": (C.c_int, [_P, _P]),
     "vdd_gemv": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "vdd_gemm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int64, _P]),
 }

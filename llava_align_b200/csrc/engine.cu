@@ -806,9 +806,16 @@ extern "C" int vdd_generate(vdd_engine* e, const int64_t* ids, int B, int T, con
   CK(cudaEventRecord(e->ev[0], st));
   if (pixels_host) {
     const size_t nb = (size_t)B * 3 * c.image_size * c.image_size * 2;
-    RC(ensure(e, e->pix, nb));
-    CK(cudaMemcpyAsync(e->pix.p, pixels_host, nb, cudaMemcpyHostToDevice, st));
-    RC(vdd_encode_images(e, e->pix.p, B, st));
+    cudaPointerAttributes pa{};
+    const bool on_device = cudaPointerGetAttributes(&pa, pixels_host) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (on_device) {  // already resident (bench.py's device-only leg)
+      RC(vdd_encode_images(e, pixels_host, B, st));
+    } else {
+      RC(ensure(e, e->pix, nb));
+      CK(cudaMemcpyAsync(e->pix.p, pixels_host, nb, cudaMemcpyHostToDevice, st));
+      RC(vdd_encode_images(e, e->pix.p, B, st));
+    }
   }
   CK(cudaEventRecord(e->ev[1], st));
   RC(vdd_prefill(e, ids, B, T, pixels_host != nullptr, use_unk, use_none, max_new, st));
@@ -922,6 +929,38 @@ extern "C" int vdd_last_timings(vdd_engine* e, float* v, float* p, float* d) {
   if (v) *v = e->t_vision;
   if (p) *p = e->t_prefill;
   if (d) *d = e->t_decode;
+  return VDD_OK;
+}
+
+// One decode step's projection launches only (qkv, o, gate_up, down per layer + lm_head), back to back exactly as in
+// the real step: bench.py times this chain with CUDA events to get the GEMV kernel's average launch duration.
+extern "C" int vdd_bench_projection_chain(vdd_engine* e, void* stream_v) {
+  if (!e || !e->prefilled) return fail(VDD_ERR_STATE, "vdd_prefill must run first");
+  if (e->R > 8) return fail(VDD_ERR_UNSUPPORTED, "projection chain is the R<=8 GEMV path");
+  cudaStream_t st = (cudaStream_t)stream_v;
+  const vdd_config& c = e->c;
+  const int H = c.hidden_size, Hl = e->Hl, Il = e->Il, R = e->R;
+  for (int l = 0; l < c.num_layers; ++l) {
+    const LayerW& w = e->lw[l];
+    GemvArgs g{};
+    g.w = w.wqkv; g.x_resid = e->resid_d; g.norm_w = w.ln1; g.eps = c.rms_eps; g.R = R; g.N = 3 * Hl; g.K = H;
+    g.epilogue = GEMV_OUT_F32; g.out_f32 = e->qkv_d; g.ld_out = 3 * Hl;
+    LK(e, launch_gemv(g, e->num_sms, e->use_pdl, st));
+    GemvArgs o{};
+    o.w = w.wo; o.x_bf16 = e->attn_d; o.R = R; o.N = H; o.K = Hl; o.epilogue = GEMV_OUT_F32; o.out_f32 = (float*)e->qkv_d; o.ld_out = H;
+    LK(e, launch_gemv(o, e->num_sms, e->use_pdl, st));
+    GemvArgs u{};
+    u.w = w.wgu; u.x_resid = e->resid_d; u.norm_w = w.ln2; u.eps = c.rms_eps; u.R = R; u.N = 2 * Il; u.K = H;
+    u.epilogue = GEMV_OUT_SWIGLU_BF16; u.out_bf16 = e->h_d; u.ld_out = Il;
+    LK(e, launch_gemv(u, e->num_sms, e->use_pdl, st));
+    GemvArgs d{};
+    d.w = w.wdown; d.x_bf16 = e->h_d; d.R = R; d.N = H; d.K = Il; d.epilogue = GEMV_OUT_F32; d.out_f32 = (float*)e->qkv_d; d.ld_out = H;
+    LK(e, launch_gemv(d, e->num_sms, e->use_pdl, st));
+  }
+  GemvArgs g{};
+  g.w = e->lm_head; g.x_resid = e->resid_d; g.norm_w = e->final_norm; g.eps = c.rms_eps; g.R = R; g.N = e->Vl; g.K = H;
+  g.epilogue = GEMV_OUT_F32; g.out_f32 = (float*)(c.tp_size > 1 ? e->logits_tp.p : e->logits.p); g.ld_out = e->Vl;
+  LK(e, launch_gemv(g, e->num_sms, e->use_pdl, st));
   return VDD_OK;
 }
 

@@ -183,10 +183,8 @@ class VddEngine:
         B, T = ids.shape
         px = None
         if images is not None:
-            px = images.detach()
-            if px.is_cuda:
-                px = px.to(torch.bfloat16).cpu()
-            px = px.to(torch.bfloat16).contiguous()
+            # host (ideally pinned) pixels are copied by the library inside the call; device pixels are used in place
+            px = images.detach().to(torch.bfloat16).contiguous()
         out = torch.empty(B, max_new_tokens, dtype=torch.int64).pin_memory()
         steps = C.c_int(0)
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
