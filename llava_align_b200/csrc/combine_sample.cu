@@ -269,10 +269,11 @@ __global__ void __launch_bounds__(CS_THREADS, 1) combine_sample_kernel(const Sam
       z += v[j];
     }
     z = block_reduce<false>(z, redf);
+    const float rz = 1.0f / z;
 #pragma unroll
     for (int j = 0; j < CS_ITEMS; ++j) {
       const int e = j * CS_THREADS + tid;
-      v[j] = e < V ? __fdiv_rn(__fdiv_rn(v[j], z), __ldg(q + e)) : -1.f;
+      v[j] = e < V ? __fdividef(v[j] * rz, __ldg(q + e)) : -1.f;  // only the ORDER of p/q matters
     }
   }
   // argmax, lowest index on ties: pack (orderable key bits, ~index) into 64 bits

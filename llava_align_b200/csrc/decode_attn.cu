@@ -6,45 +6,63 @@
 // eager softmax(QK^T/sqrt(d))V).  Rows carry their own position: main stream T+575+k,
 // unk stream T+k, none stream T-1+k.
 //
-// Grid (R*heads, max_splits), 128 threads.  Split s of row r covers tokens [s*128, min(ctx, (s+1)*128)); the
+// Grid (R*heads, max_splits), 128 threads.  Split s of row r covers tokens [s*64, min(ctx, (s+1)*64)); the
 // split that contains the new token also writes it to the cache.  Partials (m, l, o[128]) go to a workspace and
 // the last CTA to arrive for a (row, head) merges them (threadfence + counter), so the launch is self-contained.
 // HBM bytes: ctx*2*D*2 per (row, head) -- the kernel is a pure KV stream; K/V are read as 16-byte pieces, 16
-// lanes per token (256 B contiguous), 8 tokens per CTA pass.
+// lanes per token (256 B contiguous); all 16 loads of a lane are issued before any is consumed.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vdd {
 
 constexpr int DA_THREADS = 128;
-constexpr int DA_CHUNK = 128;
+constexpr int DA_CHUNK = 64;   // tokens per split: 8 groups of 16 lanes x 8 tokens each
 constexpr int DA_D = 128;
+constexpr int DA_TPG = DA_CHUNK / 8;  // tokens per 16-lane group
 
 __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAttnArgs a) {
   __shared__ float q_s[DA_D];
-  __shared__ float sc[DA_CHUNK];
+  __shared__ __align__(16) __nv_bfloat16 knew_s[DA_D];
+  __shared__ __align__(16) __nv_bfloat16 vnew_s[DA_D];
   __shared__ float o_s[8][DA_D];
-  __shared__ float red[33];
+  __shared__ float ml_s[8][2];
   __shared__ int is_last;
 
   const int rh = blockIdx.x, split = blockIdx.y;
   const int r = rh / a.heads, h = rh - r * a.heads;
   const int tid = threadIdx.x;
   const int Hl = a.heads * DA_D;
-  pdl_wait();
-  pdl_launch_dependents();
+  const int grp = tid >> 4, gl = tid & 15;
+  const int cap = a.kv_cap[r];  // written at prefill, constant during decoding: safe before the PDL wait
+  __nv_bfloat16* Kc = reinterpret_cast<__nv_bfloat16*>(a.kcache) + a.kv_off[r] + (size_t)h * cap * DA_D;
+  __nv_bfloat16* Vc = reinterpret_cast<__nv_bfloat16*>(a.vcache) + a.kv_off[r] + (size_t)h * cap * DA_D;
+  // pos and the cached tokens < pos were written by kernels that finished before the immediate predecessor (the QKV
+  // projection) could even start, so they may be read before the programmatic-dependency wait: the KV stream of this
+  // kernel overlaps the tail of the projection.
   const int pos = a.pos[r];
   const int ctx = pos + 1;
   const int nsplit = (ctx + DA_CHUNK - 1) / DA_CHUNK;
   if (split >= nsplit) return;
-  const int t0 = split * DA_CHUNK, t1 = min(ctx, t0 + DA_CHUNK), nt = t1 - t0;
-  const int cap = a.kv_cap[r];
-  __nv_bfloat16* Kc = reinterpret_cast<__nv_bfloat16*>(a.kcache) + a.kv_off[r] + (size_t)h * cap * DA_D;
-  __nv_bfloat16* Vc = reinterpret_cast<__nv_bfloat16*>(a.vcache) + a.kv_off[r] + (size_t)h * cap * DA_D;
-  const float* qkv = a.qkv + (size_t)r * 3 * Hl;
+  const int t0 = split * DA_CHUNK;
 
+  // ---- issue every K/V load of this split up front (16 x 16 B per lane in flight); the new token comes from registers
+  uint4 kr[DA_TPG], vr[DA_TPG];
+#pragma unroll
+  for (int j = 0; j < DA_TPG; ++j) {
+    const int t = t0 + grp + 8 * j;
+    kr[j] = make_uint4(0u, 0u, 0u, 0u);
+    vr[j] = kr[j];
+    if (t < pos) {
+      kr[j] = *reinterpret_cast<const uint4*>(Kc + (size_t)t * DA_D + gl * 8);
+      vr[j] = *reinterpret_cast<const uint4*>(Vc + (size_t)t * DA_D + gl * 8);
+    }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
   // ---- RoPE (rotate-half) of q; the split holding the new token also ropes k and appends k, v to the cache
   {
+    const float* qkv = a.qkv + (size_t)r * 3 * Hl;
     const int i = tid & 63;
     const float c = a.rope_cos[(size_t)pos * (DA_D / 2) + i], s = a.rope_sin[(size_t)pos * (DA_D / 2) + i];
     const float* qh = qkv + h * DA_D;
@@ -53,71 +71,73 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
     if (split == nsplit - 1) {
       const float* kh = qkv + Hl + h * DA_D;
       const float k1 = kh[i], k2 = kh[i + 64];
-      const float kr = tid < 64 ? (k1 * c - k2 * s) : (k2 * c + k1 * s);
-      Kc[(size_t)pos * DA_D + tid] = __float2bfloat16_rn(kr);
-      Vc[(size_t)pos * DA_D + tid] = __float2bfloat16_rn(qkv[2 * Hl + h * DA_D + tid]);
+      const __nv_bfloat16 kb = __float2bfloat16_rn(tid < 64 ? (k1 * c - k2 * s) : (k2 * c + k1 * s));
+      const __nv_bfloat16 vb = __float2bfloat16_rn(qkv[2 * Hl + h * DA_D + tid]);
+      Kc[(size_t)pos * DA_D + tid] = kb;
+      Vc[(size_t)pos * DA_D + tid] = vb;
+      knew_s[tid] = kb;
+      vnew_s[tid] = vb;
     }
   }
   __syncthreads();
-
-  // ---- scores: 16 lanes per token, 8 tokens per pass
-  const int grp = tid >> 4, gl = tid & 15;
   float qr[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) qr[i] = q_s[gl * 8 + i];
-#pragma unroll 4
-  for (int tt = grp; tt < DA_CHUNK; tt += 8) {
-    float s = 0.f;
-    if (tt < nt) {
-      const uint4 kv = *reinterpret_cast<const uint4*>(Kc + (size_t)(t0 + tt) * DA_D + gl * 8);
-      s = bf16lo(kv.x) * qr[0] + bf16hi(kv.x) * qr[1] + bf16lo(kv.y) * qr[2] + bf16hi(kv.y) * qr[3] +
-          bf16lo(kv.z) * qr[4] + bf16hi(kv.z) * qr[5] + bf16lo(kv.w) * qr[6] + bf16hi(kv.w) * qr[7];
+
+  // ---- per-group scores, softmax statistics and P.V entirely in registers
+  float sc[DA_TPG];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < DA_TPG; ++j) {
+    const int t = t0 + grp + 8 * j;
+    if (t == pos) {
+      kr[j] = *reinterpret_cast<const uint4*>(knew_s + gl * 8);
+      vr[j] = *reinterpret_cast<const uint4*>(vnew_s + gl * 8);
     }
+    float s = bf16lo(kr[j].x) * qr[0] + bf16hi(kr[j].x) * qr[1] + bf16lo(kr[j].y) * qr[2] + bf16hi(kr[j].y) * qr[3] +
+              bf16lo(kr[j].z) * qr[4] + bf16hi(kr[j].z) * qr[5] + bf16lo(kr[j].w) * qr[6] + bf16hi(kr[j].w) * qr[7];
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (gl == 0) sc[tt] = tt < nt ? s * a.scale : -INFINITY;
+    sc[j] = t <= pos ? s * a.scale : -INFINITY;
+    m = fmaxf(m, sc[j]);
   }
-  __syncthreads();
-
-  // ---- chunk softmax statistics
-  const float sv = sc[tid];
-  const float m = block_reduce<true>(sv, red);
-  const float pv = expf(sv - m);  // 0 for the padding
-  const float l = block_reduce<false>(pv, red);
-  sc[tid] = pv;
-  __syncthreads();
-
-  // ---- P.V: lane holds 8 dims, 8 token slots
-  float o[8];
+  float l = 0.f, o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
-#pragma unroll 4
-  for (int tt = grp; tt < DA_CHUNK; tt += 8) {
-    if (tt < nt) {
-      const uint4 vv = *reinterpret_cast<const uint4*>(Vc + (size_t)(t0 + tt) * DA_D + gl * 8);
-      const float p = sc[tt];
-      o[0] = fmaf(p, bf16lo(vv.x), o[0]); o[1] = fmaf(p, bf16hi(vv.x), o[1]);
-      o[2] = fmaf(p, bf16lo(vv.y), o[2]); o[3] = fmaf(p, bf16hi(vv.y), o[3]);
-      o[4] = fmaf(p, bf16lo(vv.z), o[4]); o[5] = fmaf(p, bf16hi(vv.z), o[5]);
-      o[6] = fmaf(p, bf16lo(vv.w), o[6]); o[7] = fmaf(p, bf16hi(vv.w), o[7]);
-    }
+#pragma unroll
+  for (int j = 0; j < DA_TPG; ++j) {
+    const float p = m == -INFINITY ? 0.f : expf(sc[j] - m);
+    l += p;
+    o[0] = fmaf(p, bf16lo(vr[j].x), o[0]); o[1] = fmaf(p, bf16hi(vr[j].x), o[1]);
+    o[2] = fmaf(p, bf16lo(vr[j].y), o[2]); o[3] = fmaf(p, bf16hi(vr[j].y), o[3]);
+    o[4] = fmaf(p, bf16lo(vr[j].z), o[4]); o[5] = fmaf(p, bf16hi(vr[j].z), o[5]);
+    o[6] = fmaf(p, bf16lo(vr[j].w), o[6]); o[7] = fmaf(p, bf16hi(vr[j].w), o[7]);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) o_s[grp][gl * 8 + i] = o[i];
+  if (gl == 0) { ml_s[grp][0] = m; ml_s[grp][1] = l; }
   __syncthreads();
-  float od = 0.f;
+  // ---- merge the 8 groups (fixed order): thread = output dim
+  float M = -INFINITY;
 #pragma unroll
-  for (int g = 0; g < 8; ++g) od += o_s[g][tid];
+  for (int g = 0; g < 8; ++g) M = fmaxf(M, ml_s[g][0]);
+  float L = 0.f, od = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float w = ml_s[g][0] == -INFINITY ? 0.f : expf(ml_s[g][0] - M);
+    L += ml_s[g][1] * w;
+    od += o_s[g][tid] * w;
+  }
 
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out_bf16) + (size_t)r * Hl + h * DA_D;
   if (nsplit == 1) {
-    out[tid] = __float2bfloat16_rn(od / l);
+    out[tid] = __float2bfloat16_rn(od / L);
     return;
   }
   // ---- park the partial, last arriver merges (fixed order over splits => deterministic)
   const size_t slot = (size_t)rh * a.max_splits + split;
   a.part_o[slot * DA_D + tid] = od;
-  if (tid == 0) { a.part_ml[slot * 2] = m; a.part_ml[slot * 2 + 1] = l; }
+  if (tid == 0) { a.part_ml[slot * 2] = M; a.part_ml[slot * 2 + 1] = L; }
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -128,16 +148,16 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  float M = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(&a.part_ml[((size_t)rh * a.max_splits + s) * 2]));
-  float L = 0.f, acc = 0.f;
+  float MM = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) MM = fmaxf(MM, __ldcg(&a.part_ml[((size_t)rh * a.max_splits + s) * 2]));
+  float LL = 0.f, acc = 0.f;
   for (int s = 0; s < nsplit; ++s) {
     const size_t sl = (size_t)rh * a.max_splits + s;
-    const float w = expf(__ldcg(&a.part_ml[sl * 2]) - M);
-    L += __ldcg(&a.part_ml[sl * 2 + 1]) * w;
+    const float w = expf(__ldcg(&a.part_ml[sl * 2]) - MM);
+    LL += __ldcg(&a.part_ml[sl * 2 + 1]) * w;
     acc += __ldcg(&a.part_o[sl * DA_D + tid]) * w;
   }
-  out[tid] = __float2bfloat16_rn(acc / L);
+  out[tid] = __float2bfloat16_rn(acc / LL);
 }
 
 cudaError_t launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t stream) {

@@ -5,14 +5,21 @@
 // here the weights are streamed ONCE for all R rows).  Algorithmic bytes = N*K*2.
 //
 // Layout: W bf16 [N, K] row-major.  Each CTA owns a contiguous band of output features; inside the CTA a warp
-// task is (4 consecutive features) x (a K-slice); a lane streams 16-byte pieces of 4 weight rows straight from
-// global memory (coalesced 512 B per warp per row, L1 no-allocate) with the next step's 8 loads in flight while
-// the current 8 are consumed; x (bf16, R rows) sits in shared memory and is reused by the 4 rows.  Partial sums
-// are reduced with a halving shuffle network, parked in shared memory and summed in a fixed order => results are
-// deterministic run to run.  Prologue options: plain bf16 x, or RMSNorm(residual) computed on the fly;
-// epilogues: fp32 store, residual +=, SwiGLU over interleaved gate/up rows.
-// With programmatic dependent launch the first weight loads are issued BEFORE griddepcontrol.wait: weights do
-// not depend on the previous kernel, so the stream of weight bytes continues across kernel boundaries.
+// task is (8 consecutive features) x (a K-slice).  Lane (g, t) = (lane/4, lane%4) streams 16-byte pieces of weight
+// row g straight from global memory (L1 no-allocate): one warp step covers 8 rows x 256 k, every row contributing
+// 512 contiguous bytes, with the next step's 8 loads per lane in flight while the current 8 are consumed.
+// The arithmetic runs on the tensor cores as mma.sync m16n8k16 (bf16 x bf16 -> fp32) with the ROLES SWAPPED: the R<=8
+// activation rows are the M side (rows R..15 are zero registers) and the 8 weight rows are the N side, so a lane's
+// 16-byte weight piece IS its B fragment for two MMAs and its 16-byte piece of x (bf16 in shared memory) IS the A
+// fragment -- the k index is permuted identically on both sides (slot pairs {2t,2t+1 | 2t+8,2t+9} <- elements
+// t*8+{0,1 | 2,3} then {4,5 | 6,7}), which a dot product does not notice.  No unpacking, no shuffles: ~6 instructions
+// per 512 weight bytes instead of ~300 on the CUDA cores, which is what moved this kernel from issue-bound to
+// HBM-bound.  (tcgen05 needs M>=64 weight rows per instruction and TMEM round trips; at 3 rows of x the legacy MMA
+// shape wastes nothing that matters -- the tensor pipe is <2% busy -- and keeps the weight stream in registers.)
+// K-slice partial sums are parked in shared memory and summed in a fixed order => deterministic.  Prologues: plain
+// bf16 x, or RMSNorm(residual) computed on the fly; epilogues: fp32 store, residual +=, SwiGLU over interleaved
+// gate/up rows.  With programmatic dependent launch the first weight loads are issued BEFORE griddepcontrol.wait:
+// weights do not depend on the previous kernel, so the stream of weight bytes continues across kernel boundaries.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -20,37 +27,15 @@ namespace vdd {
 
 constexpr int GV_THREADS = 256;
 constexpr int GV_WARPS = GV_THREADS / 32;
-constexpr int GV_RG = 4;     // weight rows per warp task
-constexpr int GV_UNIT = 256; // k elements per warp step-unit (32 lanes x 8 bf16)
+constexpr int GV_RG = 8;     // weight rows per warp task (the N side of m16n8k16)
+constexpr int GV_UNIT = 256; // k elements per warp step (8 pieces of 32 k; lane t takes 8 of each 32)
+constexpr int GV_XPAD = 32;  // bf16 elements of padding per x row: rows land 64 B apart modulo 128 (no LDS conflicts)
 
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
-
-template <int N, int O>
-struct HalvingReduce {
-  static __device__ __forceinline__ void run(float* v, int lane) {
-    if constexpr (O >= 1) {
-      if constexpr (N > 1) {
-        constexpr int h = N / 2;
-        const bool upper = (lane & O) != 0;
-#pragma unroll
-        for (int i = 0; i < h; ++i) {
-          const float send = upper ? v[i] : v[i + h];
-          const float keep = upper ? v[i + h] : v[i];
-          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
-        }
-        HalvingReduce<h, O / 2>::run(v, lane);
-      } else {
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
-        HalvingReduce<1, O / 2>::run(v, lane);
-      }
-    }
-  }
-};
-__host__ __device__ constexpr int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 struct GemvPlan {
   int n0, n1;      // CTA's feature band
@@ -72,51 +57,51 @@ __device__ __forceinline__ GemvPlan make_plan(int N, int K, int cta, int nctas) 
   return p;
 }
 
-template <int R, int UU>
-struct StepLoads {
-  uint4 w[UU][GV_RG];
-};
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  // rows 8..15 of A (registers a1, a3) are zero: only R <= 8 activation rows exist
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%5}, {%7,%8}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(0u), "r"(a2), "r"(b0), "r"(b1));
+}
 
-template <int R, int PRO, int EPI, int UU>
+template <int R, int PRO, int EPI>
 __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);                 // [R][K]
-  float* part = reinterpret_cast<float*>(smem + (size_t)R * a.K * 2);         // [nrows][ks][R]
+  const int K = a.K;
+  const int XS = K + GV_XPAD;                                                 // x row stride (elements)
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);                 // [R][XS]
+  float* part = reinterpret_cast<float*>(smem + (size_t)R * XS * 2);          // [nrows][ks][R]
   __shared__ float red[33];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int K = a.K;
+  const int g = lane >> 2, t = lane & 3;
   const GemvPlan p = make_plan(a.N, K, blockIdx.x, gridDim.x);
   const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(a.w);
 
   // ---- iterator over this warp's (task, step) sequence
   int task = warp;
-  int g = 0, j = 0, u = 0, u_end = 0;
-  auto open_task = [&](int t) {
-    g = t / p.ks;
-    j = t - g * p.ks;
+  int tg = 0, j = 0, u = 0, u_end = 0;
+  auto open_task = [&](int tk) {
+    tg = tk / p.ks;
+    j = tk - tg * p.ks;
     u = (int)(((long long)j * p.nunits) / p.ks);
     u_end = (int)(((long long)(j + 1) * p.nunits) / p.ks);
   };
-  auto load_step = [&](uint4 (&w)[UU][GV_RG], int tg, int tu, int tu_end) {
+  auto load_step = [&](uint4 (&w)[8], int ltg, int lu) {
+    int row = p.n0 + ltg * GV_RG + g;
+    row = row < p.n1 ? row : p.n1 - 1;
+    const __nv_bfloat16* wr = W + (size_t)row * K + lu * GV_UNIT + t * 8;
 #pragma unroll
-    for (int uu = 0; uu < UU; ++uu) {
-      const int k = (tu + uu) * GV_UNIT + lane * 8;
-      const bool ok = (tu + uu) < tu_end && k < K;
-#pragma unroll
-      for (int i = 0; i < GV_RG; ++i) {
-        int row = p.n0 + tg * GV_RG + i;
-        row = row < p.n1 ? row : p.n1 - 1;
-        w[uu][i] = ok ? ldg_stream(W + (size_t)row * K + k) : make_uint4(0u, 0u, 0u, 0u);
-      }
+    for (int c = 0; c < 8; ++c) {
+      const bool ok = lu * GV_UNIT + c * 32 + t * 8 < K;
+      w[c] = ok ? ldg_stream(wr + c * 32) : make_uint4(0u, 0u, 0u, 0u);
     }
   };
 
-  uint4 wc[UU][GV_RG];
-  const bool have = task < p.ntasks;
-  if (have) {
+  uint4 wc[8];
+  if (task < p.ntasks) {
     open_task(task);
-    load_step(wc, g, u, u_end);  // weights do not depend on the previous kernel: issue before the PDL wait
+    load_step(wc, tg, u);  // weights do not depend on the previous kernel: issue before the PDL wait
   }
   pdl_wait();
   pdl_launch_dependents();
@@ -146,84 +131,58 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvArgs a) {
         uint2 o;
         o.x = pack_bf16(xv.x * rstd[r] * w0, xv.y * rstd[r] * w1);
         o.y = pack_bf16(xv.z * rstd[r] * w2, xv.w * rstd[r] * w3);
-        *reinterpret_cast<uint2*>(xs + (size_t)r * K + k) = o;
+        *reinterpret_cast<uint2*>(xs + (size_t)r * XS + k) = o;
       }
     }
   } else {
-    const uint4* src = reinterpret_cast<const uint4*>(a.x_bf16);
-    uint4* dst = reinterpret_cast<uint4*>(xs);
-    for (int i = tid; i < R * K / 8; i += GV_THREADS) dst[i] = src[i];
+    const int cpr = K / 8;  // 16-byte chunks per row
+    for (int i = tid; i < R * cpr; i += GV_THREADS) {
+      const int r = i / cpr, c = i - r * cpr;
+      *reinterpret_cast<uint4*>(xs + (size_t)r * XS + c * 8) =
+          *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.x_bf16) + (size_t)r * K + c * 8);
+    }
   }
   __syncthreads();
 
-  // ---- main loop: software-pipelined over (task, step)
-  constexpr int NV = next_pow2(GV_RG * R);
-  float acc[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-
+  // ---- main loop: software-pipelined over (task, step); lane (g, t) accumulates y[r = g][features 2t, 2t+1 of the group]
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const __nv_bfloat16* xrow = xs + (size_t)(g < R ? g : 0) * XS + t * 8;
   while (task < p.ntasks) {
-    // where does the NEXT step live?
-    int ntask = task, ng = g, nu = u + UU, nu_end = u_end;
+    int ntask = task, ntg = tg, nu = u + 1, nu_end = u_end;
     bool task_done = false;
     if (nu >= u_end) {
       task_done = true;
       ntask = task + GV_WARPS;
       if (ntask < p.ntasks) {
-        ng = ntask / p.ks;
-        const int nj = ntask - ng * p.ks;
+        ntg = ntask / p.ks;
+        const int nj = ntask - ntg * p.ks;
         nu = (int)(((long long)nj * p.nunits) / p.ks);
         nu_end = (int)(((long long)(nj + 1) * p.nunits) / p.ks);
       }
     }
-    uint4 wn[UU][GV_RG];
-    if (ntask < p.ntasks) load_step(wn, ng, nu, nu_end);
+    uint4 wn[8];
+    if (ntask < p.ntasks) load_step(wn, ntg, nu);
 
-    // consume the current step
 #pragma unroll
-    for (int uu = 0; uu < UU; ++uu) {
-      const int k = (u + uu) * GV_UNIT + lane * 8;
-      if ((u + uu) < u_end && k < K) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)r * K + k);
-          const float x0 = bf16lo(xv.x), x1 = bf16hi(xv.x), x2 = bf16lo(xv.y), x3 = bf16hi(xv.y);
-          const float x4 = bf16lo(xv.z), x5 = bf16hi(xv.z), x6 = bf16lo(xv.w), x7 = bf16hi(xv.w);
-#pragma unroll
-          for (int i = 0; i < GV_RG; ++i) {
-            const uint4 wv = wc[uu][i];
-            float s = acc[i * R + r];
-            s = fmaf(bf16lo(wv.x), x0, s);
-            s = fmaf(bf16hi(wv.x), x1, s);
-            s = fmaf(bf16lo(wv.y), x2, s);
-            s = fmaf(bf16hi(wv.y), x3, s);
-            s = fmaf(bf16lo(wv.z), x4, s);
-            s = fmaf(bf16hi(wv.z), x5, s);
-            s = fmaf(bf16lo(wv.w), x6, s);
-            s = fmaf(bf16hi(wv.w), x7, s);
-            acc[i * R + r] = s;
-          }
-        }
-      }
+    for (int c = 0; c < 8; ++c) {
+      const int k = u * GV_UNIT + c * 32 + t * 8;
+      uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+      if (g < R && k < K) xv = *reinterpret_cast<const uint4*>(xrow + u * GV_UNIT + c * 32);
+      mma_bf16_16816(acc, xv.x, xv.y, wc[c].x, wc[c].y);
+      mma_bf16_16816(acc, xv.z, xv.w, wc[c].z, wc[c].w);
     }
     if (task_done) {
-      HalvingReduce<NV, 16>::run(acc, lane);
-      constexpr int LPV = 32 / NV;  // lanes per value
-      const int idx = lane / LPV;
-      if ((lane % LPV) == 0 && idx < GV_RG * R) {
-        const int i = idx / R, r = idx - i * R;
-        const int row_local = g * GV_RG + i;
-        if (p.n0 + row_local < p.n1) part[((size_t)row_local * p.ks + j) * R + r] = acc[0];
+      if (g < R) {
+        const int row_local = tg * GV_RG + 2 * t;
+        if (p.n0 + row_local < p.n1) part[((size_t)row_local * p.ks + j) * R + g] = acc[0];
+        if (p.n0 + row_local + 1 < p.n1) part[((size_t)(row_local + 1) * p.ks + j) * R + g] = acc[1];
       }
-#pragma unroll
-      for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
     }
 #pragma unroll
-    for (int uu = 0; uu < UU; ++uu)
-#pragma unroll
-      for (int i = 0; i < GV_RG; ++i) wc[uu][i] = wn[uu][i];
-    task = ntask; g = ng; u = nu; u_end = nu_end;
-    if (task_done && task < p.ntasks) j = task - g * p.ks;
+    for (int c = 0; c < 8; ++c) wc[c] = wn[c];
+    task = ntask; tg = ntg; u = nu; u_end = nu_end;
+    if (task_done && task < p.ntasks) j = task - tg * p.ks;
   }
   __syncthreads();
 
@@ -231,8 +190,8 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvArgs a) {
   const int nrows = p.n1 - p.n0;
   if constexpr (EPI == GEMV_OUT_SWIGLU_BF16) {
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
-    for (int t = tid; t < (nrows / 2) * R; t += GV_THREADS) {
-      const int pr = t / R, r = t - pr * R;
+    for (int i = tid; i < (nrows / 2) * R; i += GV_THREADS) {
+      const int pr = i / R, r = i - pr * R;
       float gsum = 0.f, usum = 0.f;
       for (int s = 0; s < p.ks; ++s) {
         gsum += part[((size_t)(2 * pr) * p.ks + s) * R + r];
@@ -242,8 +201,8 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvArgs a) {
       out[(size_t)r * a.ld_out + (p.n0 >> 1) + pr] = __float2bfloat16_rn(h);
     }
   } else {
-    for (int t = tid; t < nrows * R; t += GV_THREADS) {
-      const int row = t / R, r = t - row * R;
+    for (int i = tid; i < nrows * R; i += GV_THREADS) {
+      const int row = i / R, r = i - row * R;
       float s = 0.f;
       for (int q = 0; q < p.ks; ++q) s += part[((size_t)row * p.ks + q) * R + r];
       float* o = a.out_f32 + (size_t)r * a.ld_out + p.n0 + row;
@@ -254,7 +213,7 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvArgs a) {
 
 template <int R, int PRO, int EPI>
 static cudaError_t launch_r(const GemvArgs& a, int grid, size_t smem, bool pdl, cudaStream_t stream) {
-  auto kern = gemv_kernel<R, PRO, EPI, (R <= 4 ? 2 : 1)>;
+  auto kern = gemv_kernel<R, PRO, EPI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -287,7 +246,7 @@ cudaError_t launch_gemv(const GemvArgs& a, int num_sms, bool pdl, cudaStream_t s
   if (a.R < 1 || a.R > 8 || (a.K % 8) != 0 || (a.N % 2) != 0) return cudaErrorInvalidValue;
   const int pro = a.x_resid ? GEMV_X_RMSNORM : GEMV_X_BF16;
   // two CTAs per SM when x fits twice, else one
-  const size_t xbytes = (size_t)a.R * a.K * 2;
+  const size_t xbytes = (size_t)a.R * (a.K + GV_XPAD) * 2;
   int per_sm = xbytes <= 100 * 1024 ? 2 : 1;
   int grid = num_sms * per_sm;
   const int pairs = a.N / 2;

@@ -557,7 +557,7 @@ extern "C" int vdd_prefill(vdd_engine* e, const int64_t* ids, int B, int T, int 
   const int Mtot = (int)tok.size();
   e->B = B; e->T = T; e->S = S; e->R = R; e->Mtot = Mtot; e->max_new = max_new; e->max_len = max_len;
   e->kv_layer_stride = kv_total;
-  e->max_splits = (max_len + max_new + 127) / 128;
+  e->max_splits = (max_len + max_new + 63) / 64;
 
   // ---- buffers
   RC(ensure(e, e->resid, (size_t)Mtot * H * 4));
