@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: libvdd.so loads, exports every symbol include/vdd.h declares, its ctypes
+structs match the header, and the product path refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header():
+    return open(os.path.join(ROOT, "include", "vdd.h")).read()
+
+
+def test_library_exports_every_declared_symbol():
+    from llava_align_b200 import _lib
+    declared = set(re.findall(r"VDD_API\s+[\w\s\*]+?\b(vdd_\w+)\s*\(", _header()))
+    assert len(declared) >= 20
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"libvdd.so does not export {name}"
+    # and the Python binding declares a signature for each of them
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.vdd_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    from llava_align_b200 import _lib
+    h = _header()
+    cfg_body = re.search(r"typedef struct vdd_config \{(.*?)\} vdd_config;", h, re.S).group(1)
+    fields = []
+    for decl in re.findall(r"(int32_t|float)\s+([^;]+);", cfg_body):
+        fields += [(n.strip(), decl[0]) for n in decl[1].split(",")]
+    got = [(n, "float" if t is C.c_float else "int32_t") for n, t in _lib.vdd_config._fields_]
+    assert got == fields
+    sp_body = re.search(r"typedef struct vdd_sample_params \{(.*?)\} vdd_sample_params;", h, re.S).group(1)
+    sp = [(n, t) for t, n in re.findall(r"(int32_t|int64_t|float)\s+(\w+);", sp_body)]
+    names = {C.c_float: "float", C.c_int32: "int32_t", C.c_int64: "int64_t"}
+    assert [(n, names[t]) for n, t in _lib.vdd_sample_params._fields_] == sp
+    assert C.sizeof(_lib.vdd_sample_params) == 40
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from llava_align_b200 import _lib
+    from llava_align_b200.config import tiny_config
+    from llava_align_b200.model import LlavaLlamaForCausalLM
+    with pytest.raises(_lib.VddError):
+        LlavaLlamaForCausalLM(tiny_config(), "cuda:0")
+    lib = _lib.load()
+    h = C.c_void_p()
+    c = _lib.vdd_config()
+    assert lib.vdd_create(C.byref(c), C.byref(h)) != 0
+    assert b"CUDA device" in lib.vdd_last_error()
+
+
+def test_product_path_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "llava_align_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{fn} imports the oracle"
+            assert "vdd_oracle" not in src and "cpu_baseline" not in src, fn
+    assert not re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(ROOT, "vcd_utils", "vcd_sample.py")).read(), re.M)
+
+
+def test_generate_kwarg_surface():
+    """The kwargs the reference drivers pass (llava_sampling.py:96-109, llava_calibrate.py:160-177) are all accepted."""
+    import inspect
+    from llava_align_b200.model import LlavaLlamaForCausalLM, evolve_vcd_sampling, vdd_sampler_installed
+    sig = inspect.signature(LlavaLlamaForCausalLM.generate)
+    for k in ("input_ids", "images", "images_cd", "cd_alpha", "cd_beta", "use_dd", "use_dd_unk", "max_new_tokens", "use_cache",
+              "num_beams"):
+        assert k in sig.parameters
+    evolve_vcd_sampling()
+    evolve_vcd_sampling()  # idempotent
+    assert vdd_sampler_installed()
+    from vcd_utils.vcd_sample import evolve_vcd_sampling as e2  # the reference's import path
+    assert e2 is evolve_vcd_sampling

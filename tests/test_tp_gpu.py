@@ -1,0 +1,72 @@
+"""Tensor-parallel engine on 2 GPUs (NCCL over NVLink) == the single-GPU engine: greedy VDD tokens identical, stream logits
+within fp32 re-association noise.  Needs >= 2 CUDA devices (run with `gpurun --gpus 2`)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from helpers import make_inputs, tiny_model
+    from llava_align_b200 import engine as E
+    from llava_align_b200.model import LlavaLlamaForCausalLM, evolve_vcd_sampling
+    cfg, sd, oracle = tiny_model(0)
+    evolve_vcd_sampling()
+    m = LlavaLlamaForCausalLM(cfg, f"cuda:{rank}", tp_size=world, tp_rank=rank)
+    m.load_state_dict(sd)
+    idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{rank}")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(E.VddEngine.tp_unique_id()), dtype=torch.uint8).to(f"cuda:{rank}")
+    dist.broadcast(idt, 0)
+    m.engine.tp_init(bytes(idt.cpu().numpy().tobytes()))
+    ids, img = make_inputs(cfg, 2, 12, 9)
+    n = 6
+    m.engine.encode_images(img)
+    lg = m.engine.prefill(ids, True, True, False, n).cpu().clone()
+    out = m.generate(ids.cuda(rank), images=img.cuda(rank), use_dd_unk=True, cd_alpha=1.0, cd_beta=0.1, do_sample=True, top_k=1,
+                     max_new_tokens=n, eos_token_id=None)
+    ret[rank] = (lg, out.cpu())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_tp2_equals_tp1():
+    from helpers import make_inputs, tiny_model
+    from llava_align_b200.model import LlavaLlamaForCausalLM, evolve_vcd_sampling
+    cfg, sd, oracle = tiny_model(0)
+    evolve_vcd_sampling()
+    m = LlavaLlamaForCausalLM(cfg, "cuda:0")
+    m.load_state_dict(sd)
+    ids, img = make_inputs(cfg, 2, 12, 9)
+    n = 6
+    m.engine.encode_images(img)
+    lg1 = m.engine.prefill(ids, True, True, False, n).cpu().clone()
+    out1 = m.generate(ids.cuda(), images=img.cuda(), use_dd_unk=True, cd_alpha=1.0, cd_beta=0.1, do_sample=True, top_k=1,
+                      max_new_tokens=n, eos_token_id=None).cpu()
+    del m
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for r in range(2):
+        lg, out = ret[r]
+        assert (lg - lg1).abs().max().item() < 2e-2
+        assert torch.equal(out, out1)
