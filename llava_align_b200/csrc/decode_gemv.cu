@@ -29,6 +29,7 @@ constexpr int GV_THREADS = 256;
 constexpr int GV_WARPS = GV_THREADS / 32;
 constexpr int GV_RG = 8;     // weight rows per warp task (the N side of m16n8k16)
 constexpr int GV_UNIT = 256; // k elements per warp step (8 pieces of 32 k; lane t takes 8 of each 32)
+constexpr int GV_MAX_TASKS = 256;
 constexpr int GV_XPAD = 32;  // bf16 elements of padding per x row: rows land 64 B apart modulo 128 (no LDS conflicts)
 
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
@@ -78,29 +79,36 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvArgs a) {
   const GemvPlan p = make_plan(a.N, K, blockIdx.x, gridDim.x);
   const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(a.w);
 
-  // ---- iterator over this warp's (task, step) sequence
+  // ---- task table: (row group, first unit, end unit, k-slice) per task, computed once (the divisions stay out of the
+  //      streaming loop, whose instruction count per 4 KB step is what bounds a warp's bandwidth)
+  __shared__ int4 task_tab[GV_MAX_TASKS];
+  for (int i = tid; i < p.ntasks; i += GV_THREADS) {
+    const int gi = i / p.ks, ji = i - gi * p.ks;
+    task_tab[i] = make_int4(gi, (ji * p.nunits) / p.ks, ((ji + 1) * p.nunits) / p.ks, ji);
+  }
+  __syncthreads();
   int task = warp;
   int tg = 0, j = 0, u = 0, u_end = 0;
-  auto open_task = [&](int tk) {
-    tg = tk / p.ks;
-    j = tk - tg * p.ks;
-    u = (int)(((long long)j * p.nunits) / p.ks);
-    u_end = (int)(((long long)(j + 1) * p.nunits) / p.ks);
-  };
   auto load_step = [&](uint4 (&w)[8], int ltg, int lu) {
     int row = p.n0 + ltg * GV_RG + g;
     row = row < p.n1 ? row : p.n1 - 1;
     const __nv_bfloat16* wr = W + (size_t)row * K + lu * GV_UNIT + t * 8;
+    if ((lu + 1) * GV_UNIT <= K) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const bool ok = lu * GV_UNIT + c * 32 + t * 8 < K;
-      w[c] = ok ? ldg_stream(wr + c * 32) : make_uint4(0u, 0u, 0u, 0u);
+      for (int c = 0; c < 8; ++c) w[c] = ldg_stream(wr + c * 32);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const bool ok = lu * GV_UNIT + c * 32 + t * 8 < K;
+        w[c] = ok ? ldg_stream(wr + c * 32) : make_uint4(0u, 0u, 0u, 0u);
+      }
     }
   };
 
   uint4 wc[8];
   if (task < p.ntasks) {
-    open_task(task);
+    const int4 tk = task_tab[task];
+    tg = tk.x; u = tk.y; u_end = tk.z; j = tk.w;
     load_step(wc, tg, u);  // weights do not depend on the previous kernel: issue before the PDL wait
   }
   pdl_wait();
@@ -145,44 +153,46 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvArgs a) {
   __syncthreads();
 
   // ---- main loop: software-pipelined over (task, step); lane (g, t) accumulates y[r = g][features 2t, 2t+1 of the group]
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};  // two independent MMA chains
   const __nv_bfloat16* xrow = xs + (size_t)(g < R ? g : 0) * XS + t * 8;
   while (task < p.ntasks) {
-    int ntask = task, ntg = tg, nu = u + 1, nu_end = u_end;
+    int ntask = task, ntg = tg, nu = u + 1, nu_end = u_end, nj = j;
     bool task_done = false;
     if (nu >= u_end) {
       task_done = true;
       ntask = task + GV_WARPS;
       if (ntask < p.ntasks) {
-        ntg = ntask / p.ks;
-        const int nj = ntask - ntg * p.ks;
-        nu = (int)(((long long)nj * p.nunits) / p.ks);
-        nu_end = (int)(((long long)(nj + 1) * p.nunits) / p.ks);
+        const int4 tk = task_tab[ntask];
+        ntg = tk.x; nu = tk.y; nu_end = tk.z; nj = tk.w;
       }
     }
     uint4 wn[8];
     if (ntask < p.ntasks) load_step(wn, ntg, nu);
 
+    {
+      const __nv_bfloat16* xp = xrow + u * GV_UNIT;
+      const bool full = (u + 1) * GV_UNIT <= K;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int k = u * GV_UNIT + c * 32 + t * 8;
-      uint4 xv = make_uint4(0u, 0u, 0u, 0u);
-      if (g < R && k < K) xv = *reinterpret_cast<const uint4*>(xrow + u * GV_UNIT + c * 32);
-      mma_bf16_16816(acc, xv.x, xv.y, wc[c].x, wc[c].y);
-      mma_bf16_16816(acc, xv.z, xv.w, wc[c].z, wc[c].w);
+      for (int c = 0; c < 8; ++c) {
+        // lanes with g >= R read row 0: their products land in accumulator rows nobody stores
+        uint4 xv = make_uint4(0u, 0u, 0u, 0u);
+        if (full || u * GV_UNIT + c * 32 + t * 8 < K) xv = *reinterpret_cast<const uint4*>(xp + c * 32);
+        mma_bf16_16816(acc, xv.x, xv.y, wc[c].x, wc[c].y);
+        mma_bf16_16816(acc2, xv.z, xv.w, wc[c].z, wc[c].w);
+      }
     }
     if (task_done) {
       if (g < R) {
         const int row_local = tg * GV_RG + 2 * t;
-        if (p.n0 + row_local < p.n1) part[((size_t)row_local * p.ks + j) * R + g] = acc[0];
-        if (p.n0 + row_local + 1 < p.n1) part[((size_t)(row_local + 1) * p.ks + j) * R + g] = acc[1];
+        if (p.n0 + row_local < p.n1) part[((size_t)row_local * p.ks + j) * R + g] = acc[0] + acc2[0];
+        if (p.n0 + row_local + 1 < p.n1) part[((size_t)(row_local + 1) * p.ks + j) * R + g] = acc[1] + acc2[1];
       }
       acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+      acc2[0] = acc2[1] = acc2[2] = acc2[3] = 0.f;
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) wc[c] = wn[c];
-    task = ntask; tg = ntg; u = nu; u_end = nu_end;
-    if (task_done && task < p.ntasks) j = task - tg * p.ks;
+    task = ntask; tg = ntg; u = nu; u_end = nu_end; j = nj;
   }
   __syncthreads();
 
