@@ -118,6 +118,8 @@ VDD_API int vdd_tp_init(vdd_engine* e, const void* id128_host);
 VDD_API int64_t vdd_launch_count(vdd_engine* e, int reset);
 VDD_API int vdd_last_timings(vdd_engine* e, float* vision_ms, float* prefill_ms, float* decode_ms);
 
+/* Debug (VDD_TRACE=1): globaltimer stamps [148 CTAs][4 phases][6 events] of the middle layer's fused projection chain. */
+VDD_API int vdd_debug_trace(vdd_engine* e, unsigned long long* out_host, int n);
 /* Enqueue one decode step's projection kernels only (4 per layer + lm_head), for bench.py's roofline leg. */
 VDD_API int vdd_bench_projection_chain(vdd_engine* e, void* stream);
 

@@ -55,6 +55,7 @@ SIGNATURES = {
     "vdd_launch_count": (C.c_int64, [_P, C.c_int]),
     "vdd_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "vdd_bench_projection_chain": (C.c_int, [_P, _P]),
+    "vdd_debug_trace": (C.c_int, [_P, _P, C.c_int]),
     "vdd_gemv": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "vdd_gemm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int64, _P]),
 }

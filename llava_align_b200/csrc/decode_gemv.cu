@@ -6,8 +6,10 @@
 //
 // Layout: W bf16 [N, K] row-major.  Each CTA owns a contiguous band of output features; inside the CTA a warp
 // task is (8 consecutive features) x (a K-slice).  Lane (g, t) = (lane/4, lane%4) streams 16-byte pieces of weight
-// row g straight from global memory (L1 no-allocate): one warp step covers 8 rows x 256 k, every row contributing
-// 512 contiguous bytes, with the next step's 8 loads per lane in flight while the current 8 are consumed.
+// row g with cp.async (16 B, L1 bypass) into a PRIVATE shared-memory ring of 3 steps per warp: one warp step covers
+// 8 rows x 256 k (every row contributing 512 contiguous bytes), two steps (8 KB per warp, 128 KB per SM) are always in
+// flight while the third is consumed, and since a lane only ever reads back the bytes it requested itself the ring
+// needs no barrier at all -- cp.async.wait_group is the only synchronisation in the stream loop.
 // The arithmetic runs on the tensor cores as mma.sync m16n8k16 (bf16 x bf16 -> fp32) with the ROLES SWAPPED: the R<=8
 // activation rows are the M side (rows R..15 are zero registers) and the 8 weight rows are the N side, so a lane's
 // 16-byte weight piece IS its B fragment for two MMAs and its 16-byte piece of x (bf16 in shared memory) IS the A
@@ -18,31 +20,38 @@
 // shape wastes nothing that matters -- the tensor pipe is <2% busy -- and keeps the weight stream in registers.)
 // K-slice partial sums are parked in shared memory and summed in a fixed order => deterministic.  Prologues: plain
 // bf16 x, or RMSNorm(residual) computed on the fly; epilogues: fp32 store, residual +=, SwiGLU over interleaved
-// gate/up rows.  With programmatic dependent launch the first weight loads are issued BEFORE griddepcontrol.wait:
-// weights do not depend on the previous kernel, so the stream of weight bytes continues across kernel boundaries.
+// gate/up rows.  With programmatic dependent launch the first TWO steps of every warp (128 KB per SM) are requested
+// BEFORE griddepcontrol.wait: weights do not depend on the previous kernel, so HBM stays busy while the previous
+// kernel drains and while this one normalises / stages x.
+//
+// FUSED CHAIN: one launch can run up to four projections back to back (o -> gate_up -> down -> next layer's qkv), with a
+// grid-wide barrier (one atomic counter per boundary, all 148 CTAs co-resident at one CTA per SM) where a kernel
+// boundary used to be.  The next projection's first ring steps are requested BEFORE the barrier -- weights never
+// depend on activations -- so the weight stream does not stop while CTAs wait for each other; that removes two thirds
+// of the launch boundaries of a decode step (the probe in tools/stream_probe.cu shows a chain of 129 separate
+// read-only kernels cannot exceed ~0.87 of the copy bandwidth on this part, whatever the kernel does).
+// Activations produced by other CTAs are read with ld.global.cg (L2) because L1 is not coherent across a grid barrier.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vdd {
 
-constexpr int GV_THREADS = 256;
-constexpr int GV_WARPS = GV_THREADS / 32;
-constexpr int GV_RG = 8;     // weight rows per warp task (the N side of m16n8k16)
-constexpr int GV_UNIT = 256; // k elements per warp step (8 pieces of 32 k; lane t takes 8 of each 32)
+constexpr int GV_RG = 8;      // weight rows per warp task (the N side of m16n8k16)
+constexpr int GV_UNIT = 256;  // k elements per warp step (8 pieces of 32 k; lane t takes 8 of each 32)
+constexpr int GV_D = 3;       // ring depth in steps per warp (GV_D - 1 steps in flight)
+constexpr int GV_STEP_BYTES = GV_RG * GV_UNIT * 2;  // 4 KB
+constexpr int GV_MAX_WARPS = 16;
 constexpr int GV_MAX_TASKS = 256;
-constexpr int GV_XPAD = 32;  // bf16 elements of padding per x row: rows land 64 B apart modulo 128 (no LDS conflicts)
-
-__device__ __forceinline__ uint4 ldg_stream(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
+constexpr int GV_XPAD = 32;   // bf16 elements of padding per x row: rows land 64 B apart modulo 128 (no LDS conflicts)
+constexpr int GV_SMEM_BUDGET = 216 * 1024;
 
 struct GemvPlan {
-  int n0, n1;      // CTA's feature band
+  int n0, n1;  // CTA's feature band
   int ngroups, ks, ntasks, nunits;
 };
-__device__ __forceinline__ GemvPlan make_plan(int N, int K, int cta, int nctas) {
+__host__ __device__ __forceinline__ GemvPlan make_plan(int N, int K, int cta, int nctas, int nwarps) {
   GemvPlan p;
   const int pairs = N >> 1;
   p.n0 = 2 * (int)(((long long)cta * pairs) / nctas);
@@ -50,7 +59,7 @@ __device__ __forceinline__ GemvPlan make_plan(int N, int K, int cta, int nctas) 
   const int nrows = p.n1 - p.n0;
   p.ngroups = (nrows + GV_RG - 1) / GV_RG;
   p.nunits = (K + GV_UNIT - 1) / GV_UNIT;
-  int ks = p.ngroups > 0 ? (4 * GV_WARPS + p.ngroups - 1) / p.ngroups : 1;
+  int ks = p.ngroups > 0 ? (4 * nwarps + p.ngroups - 1) / p.ngroups : 1;
   const int ksmax = p.nunits / 2 > 1 ? p.nunits / 2 : 1;
   ks = ks < 1 ? 1 : (ks > ksmax ? ksmax : ks);
   p.ks = ks;
@@ -64,143 +73,251 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(0u), "r"(a2), "r"(b0), "r"(b1));
 }
-
-template <int R, int PRO, int EPI>
-__global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int K = a.K;
-  const int XS = K + GV_XPAD;                                                 // x row stride (elements)
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem);                 // [R][XS]
-  float* part = reinterpret_cast<float*>(smem + (size_t)R * XS * 2);          // [nrows][ks][R]
-  __shared__ float red[33];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const GemvPlan p = make_plan(a.N, K, blockIdx.x, gridDim.x);
-  const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(a.w);
-
-  // ---- task table: (row group, first unit, end unit, k-slice) per task, computed once (the divisions stay out of the
-  //      streaming loop, whose instruction count per 4 KB step is what bounds a warp's bandwidth)
-  __shared__ int4 task_tab[GV_MAX_TASKS];
-  for (int i = tid; i < p.ntasks; i += GV_THREADS) {
-    const int gi = i / p.ks, ji = i - gi * p.ks;
-    task_tab[i] = make_int4(gi, (ji * p.nunits) / p.ks, ((ji + 1) * p.nunits) / p.ks, ji);
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Grid barrier, split in two so that the next projection's weight requests are issued between arrive and wait.
+// All CTAs of the grid are co-resident (grid <= #SMs, one CTA per SM); bounded spin => a bug traps instead of hanging.
+__device__ __forceinline__ void grid_arrive(unsigned* counter) {
+  __syncthreads();  // every thread's global stores of this phase are issued
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+  }
+}
+__device__ __forceinline__ void grid_wait(const unsigned* counter, unsigned target) {
+  if (threadIdx.x == 0) {
+    unsigned spins = 0;
+    while (ld_acquire_u32(counter) < target) {
+      if (++spins > (1u << 22)) __trap();
+    }
   }
   __syncthreads();
-  int task = warp;
-  int tg = 0, j = 0, u = 0, u_end = 0;
-  auto load_step = [&](uint4 (&w)[8], int ltg, int lu) {
-    int row = p.n0 + ltg * GV_RG + g;
-    row = row < p.n1 ? row : p.n1 - 1;
-    const __nv_bfloat16* wr = W + (size_t)row * K + lu * GV_UNIT + t * 8;
-    if ((lu + 1) * GV_UNIT <= K) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) w[c] = ldg_stream(wr + c * 32);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const bool ok = lu * GV_UNIT + c * 32 + t * 8 < K;
-        w[c] = ok ? ldg_stream(wr + c * 32) : make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-  };
+}
 
-  uint4 wc[8];
-  if (task < p.ntasks) {
-    const int4 tk = task_tab[task];
-    tg = tk.x; u = tk.y; u_end = tk.z; j = tk.w;
-    load_step(wc, tg, u);  // weights do not depend on the previous kernel: issue before the PDL wait
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define GV_TRACE(ev)                                                                                  \
+  do {                                                                                                \
+    if (trace && threadIdx.x == 0) trace[((size_t)blockIdx.x * 4 + ph) * 8 + (ev)] = gtime();         \
+  } while (0)
+
+// position of a warp inside its (task, step) sequence
+struct GemvIter {
+  int task, tg, u, u_end, j;
+};
+struct GemvCtx {
+  GemvPlan p;
+  GemvIter pi, ci;
+  int4* task_tab;
+  uint32_t my_ring;  // shared-space address of this lane's 16 bytes in slot 0 of its warp's ring
+  int nwarps, g, t;
+};
+__device__ __forceinline__ void it_open(const GemvCtx& c, GemvIter& it, int task) {
+  it.task = task;
+  if (task < c.p.ntasks) {
+    const int4 tk = c.task_tab[task];
+    it.tg = tk.x; it.u = tk.y; it.u_end = tk.z; it.j = tk.w;
   }
-  pdl_wait();
-  pdl_launch_dependents();
-
-  // ---- prologue: stage x (bf16) in shared memory
-  if constexpr (PRO == GEMV_X_RMSNORM) {
-    const __nv_bfloat16* nw = reinterpret_cast<const __nv_bfloat16*>(a.norm_w);
-    float ss[R];
+}
+__device__ __forceinline__ void it_advance(const GemvCtx& c, GemvIter& it) {
+  if (++it.u >= it.u_end) it_open(c, it, it.task + c.nwarps);
+}
+// request one step (8 x 16 B per lane) into ring slot `slot`; always commits a group so the counting stays uniform
+__device__ __forceinline__ void ring_request(const GemvCtx& c, const __nv_bfloat16* W, int K, const GemvIter& it, int slot) {
+  if (it.task < c.p.ntasks) {
+    int row = c.p.n0 + it.tg * GV_RG + c.g;
+    row = row < c.p.n1 ? row : c.p.n1 - 1;
+    const int k0 = it.u * GV_UNIT + c.t * 8;
+    const __nv_bfloat16* wr = W + (size_t)row * K + k0;
+    const uint32_t dst = c.my_ring + (uint32_t)slot * GV_STEP_BYTES;
 #pragma unroll
-    for (int r = 0; r < R; ++r) ss[r] = 0.f;
-    for (int k = tid * 4; k < K; k += GV_THREADS * 4) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float4 xv = *reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k);
-        ss[r] += xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
-      }
+    for (int q = 0; q < 8; ++q) {
+      const bool ok = k0 + q * 32 < K;  // ragged K (tensor-parallel slices): zero-fill
+      cp_async16(dst + q * 512, ok ? (const void*)(wr + q * 32) : (const void*)W, ok ? 16u : 0u);
     }
-    float rstd[R];
+  }
+  cp_async_commit();
+}
+
+// Part 1 of a projection: plan, task table, first GV_D-1 ring steps.  Touches only weights (never activations).
+__device__ __forceinline__ void phase_begin(const GemvArgs& a, GemvCtx& c) {
+  const int tid = threadIdx.x, nthreads = blockDim.x, warp = tid >> 5;
+  c.p = make_plan(a.N, a.K, blockIdx.x, gridDim.x, c.nwarps);
+  for (int i = tid; i < c.p.ntasks; i += nthreads) {
+    const int gi = i / c.p.ks, ji = i - gi * c.p.ks;
+    c.task_tab[i] = make_int4(gi, (ji * c.p.nunits) / c.p.ks, ((ji + 1) * c.p.nunits) / c.p.ks, ji);
+  }
+  __syncthreads();
+  it_open(c, c.pi, warp);
+  c.ci = c.pi;
+  const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(a.w);
 #pragma unroll
-    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(block_reduce<false>(ss[r], red) / (float)K + a.eps);
-    for (int k = tid * 4; k < K; k += GV_THREADS * 4) {
-      const uint2 wv = *reinterpret_cast<const uint2*>(nw + k);
-      const float w0 = bf16lo(wv.x), w1 = bf16hi(wv.x), w2 = bf16lo(wv.y), w3 = bf16hi(wv.y);
+  for (int s = 0; s < GV_D - 1; ++s) {
+    ring_request(c, W, a.K, c.pi, s);
+    if (c.pi.task < c.p.ntasks) it_advance(c, c.pi);
+  }
+}
+
+// Part 2: stage x, stream the rest of the weights, reduce, epilogue.  Prologue / epilogue kinds are runtime switches
+// around ONE copy of the stream loop (a fused chain runs four projections through the same instructions).
+template <int R>
+__device__ __forceinline__ void phase_rest(const GemvArgs& a, GemvCtx& c, unsigned char* smem, float* red,
+                                           unsigned long long* trace, int ph) {
+  const int K = a.K;
+  const int XS = K + GV_XPAD;  // x row stride (elements)
+  const int nthreads = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = c.g, t = c.t;
+  const GemvPlan& p = c.p;
+  const int epi = a.epilogue;
+  unsigned char* ring = smem;                                                                              // [nwarps][GV_D][4 KB]
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)c.nwarps * GV_D * GV_STEP_BYTES);  // [R][XS]
+  float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(xs) + (size_t)R * XS * 2);       // [nrows][ks][R]
+  const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(a.w);
+  const int nrows = p.n1 - p.n0;
+
+  // residual value this thread will add to (fetched now, needed after the stream loop)
+  float resid_old = 0.f;
+  if (epi == GEMV_OUT_ADD_RESID && tid < nrows * R) {
+    const int row = tid / R, r = tid - row * R;
+    resid_old = __ldcg(a.out_f32 + (size_t)r * a.ld_out + p.n0 + row);
+  }
+  // ---- prologue: stage x (bf16) in shared memory.  Loads go to L2 (.cg): the producer may be another CTA of this launch.
+  if (a.x_resid) {
+    const __nv_bfloat16* nw = reinterpret_cast<const __nv_bfloat16*>(a.norm_w);
+    constexpr int PASS = R <= 3 ? 4 : (R <= 4 ? 3 : 1);  // float4 per thread per row held in registers
+    if (K <= PASS * 4 * nthreads) {
+      float4 xv[R][PASS];
+      float ss[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float4 xv = *reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k);
-        uint2 o;
-        o.x = pack_bf16(xv.x * rstd[r] * w0, xv.y * rstd[r] * w1);
-        o.y = pack_bf16(xv.z * rstd[r] * w2, xv.w * rstd[r] * w3);
-        *reinterpret_cast<uint2*>(xs + (size_t)r * XS + k) = o;
+        ss[r] = 0.f;
+#pragma unroll
+        for (int q = 0; q < PASS; ++q) {
+          const int k = (q * nthreads + tid) * 4;
+          xv[r][q] = k < K ? __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int q = 0; q < PASS; ++q)
+          ss[r] += xv[r][q].x * xv[r][q].x + xv[r][q].y * xv[r][q].y + xv[r][q].z * xv[r][q].z + xv[r][q].w * xv[r][q].w;
+      float rstd[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(block_reduce<false>(ss[r], red) / (float)K + a.eps);
+#pragma unroll
+      for (int q = 0; q < PASS; ++q) {
+        const int k = (q * nthreads + tid) * 4;
+        if (k < K) {
+          const uint2 wv = *reinterpret_cast<const uint2*>(nw + k);
+          const float w0 = bf16lo(wv.x), w1 = bf16hi(wv.x), w2 = bf16lo(wv.y), w3 = bf16hi(wv.y);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            uint2 o;
+            o.x = pack_bf16(xv[r][q].x * rstd[r] * w0, xv[r][q].y * rstd[r] * w1);
+            o.y = pack_bf16(xv[r][q].z * rstd[r] * w2, xv[r][q].w * rstd[r] * w3);
+            *reinterpret_cast<uint2*>(xs + (size_t)r * XS + k) = o;
+          }
+        }
+      }
+    } else {  // wide rows: two passes over L2
+      float ss[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) ss[r] = 0.f;
+      for (int k = tid * 4; k < K; k += nthreads * 4) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 xv = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k));
+          ss[r] += xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
+        }
+      }
+      float rstd[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(block_reduce<false>(ss[r], red) / (float)K + a.eps);
+      for (int k = tid * 4; k < K; k += nthreads * 4) {
+        const uint2 wv = *reinterpret_cast<const uint2*>(nw + k);
+        const float w0 = bf16lo(wv.x), w1 = bf16hi(wv.x), w2 = bf16lo(wv.y), w3 = bf16hi(wv.y);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 xv = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k));
+          uint2 o;
+          o.x = pack_bf16(xv.x * rstd[r] * w0, xv.y * rstd[r] * w1);
+          o.y = pack_bf16(xv.z * rstd[r] * w2, xv.w * rstd[r] * w3);
+          *reinterpret_cast<uint2*>(xs + (size_t)r * XS + k) = o;
+        }
       }
     }
   } else {
+    // bf16 x: asynchronous 16-byte copies straight into shared memory, all in flight at once
     const int cpr = K / 8;  // 16-byte chunks per row
-    for (int i = tid; i < R * cpr; i += GV_THREADS) {
-      const int r = i / cpr, c = i - r * cpr;
-      *reinterpret_cast<uint4*>(xs + (size_t)r * XS + c * 8) =
-          *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.x_bf16) + (size_t)r * K + c * 8);
+    const __nv_bfloat16* xg = reinterpret_cast<const __nv_bfloat16*>(a.x_bf16);
+    for (int i = tid; i < R * cpr; i += nthreads) {
+      const int r = i / cpr, q = i - r * cpr;
+      cp_async16(smem_u32(xs + (size_t)r * XS + q * 8), xg + (size_t)r * K + q * 8, 16u);
     }
+    cp_async_commit();
+    cp_async_wait<0>();  // (also drains the ring steps requested in phase_begin, which are needed next anyway)
   }
   __syncthreads();
+  GV_TRACE(2);
 
-  // ---- main loop: software-pipelined over (task, step); lane (g, t) accumulates y[r = g][features 2t, 2t+1 of the group]
+  // ---- stream loop; lane (g, t) accumulates y[r = g][features 2t, 2t+1 of the group]
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};  // two independent MMA chains
+  // lanes with g >= R read x row 0: their products land in accumulator rows nobody stores
   const __nv_bfloat16* xrow = xs + (size_t)(g < R ? g : 0) * XS + t * 8;
-  while (task < p.ntasks) {
-    int ntask = task, ntg = tg, nu = u + 1, nu_end = u_end, nj = j;
-    bool task_done = false;
-    if (nu >= u_end) {
-      task_done = true;
-      ntask = task + GV_WARPS;
-      if (ntask < p.ntasks) {
-        const int4 tk = task_tab[ntask];
-        ntg = tk.x; nu = tk.y; nu_end = tk.z; nj = tk.w;
-      }
-    }
-    uint4 wn[8];
-    if (ntask < p.ntasks) load_step(wn, ntg, nu);
-
+  int cslot = 0, pslot = GV_D - 1;
+  while (c.ci.task < p.ntasks) {
+    ring_request(c, W, K, c.pi, pslot);
+    if (c.pi.task < p.ntasks) it_advance(c, c.pi);
+    cp_async_wait<GV_D - 1>();  // everything but the newest GV_D-1 groups has landed: the step to consume is there
     {
-      const __nv_bfloat16* xp = xrow + u * GV_UNIT;
-      const bool full = (u + 1) * GV_UNIT <= K;
+      const uint4* wq = reinterpret_cast<const uint4*>(ring + (size_t)(warp * GV_D + cslot) * GV_STEP_BYTES) + lane;
+      const __nv_bfloat16* xp = xrow + c.ci.u * GV_UNIT;
+      const bool full = (c.ci.u + 1) * GV_UNIT <= K;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        // lanes with g >= R read row 0: their products land in accumulator rows nobody stores
+      for (int q = 0; q < 8; ++q) {
+        const uint4 wv = wq[q * 32];
         uint4 xv = make_uint4(0u, 0u, 0u, 0u);
-        if (full || u * GV_UNIT + c * 32 + t * 8 < K) xv = *reinterpret_cast<const uint4*>(xp + c * 32);
-        mma_bf16_16816(acc, xv.x, xv.y, wc[c].x, wc[c].y);
-        mma_bf16_16816(acc2, xv.z, xv.w, wc[c].z, wc[c].w);
+        if (full || c.ci.u * GV_UNIT + q * 32 + t * 8 < K) xv = *reinterpret_cast<const uint4*>(xp + q * 32);
+        mma_bf16_16816(acc, xv.x, xv.y, wv.x, wv.y);
+        mma_bf16_16816(acc2, xv.z, xv.w, wv.z, wv.w);
       }
     }
-    if (task_done) {
+    if (c.ci.u + 1 >= c.ci.u_end) {  // task complete: park its partial sums
       if (g < R) {
-        const int row_local = tg * GV_RG + 2 * t;
-        if (p.n0 + row_local < p.n1) part[((size_t)row_local * p.ks + j) * R + g] = acc[0] + acc2[0];
-        if (p.n0 + row_local + 1 < p.n1) part[((size_t)(row_local + 1) * p.ks + j) * R + g] = acc[1] + acc2[1];
+        const int row_local = c.ci.tg * GV_RG + 2 * t;
+        if (p.n0 + row_local < p.n1) part[((size_t)row_local * p.ks + c.ci.j) * R + g] = acc[0] + acc2[0];
+        if (p.n0 + row_local + 1 < p.n1) part[((size_t)(row_local + 1) * p.ks + c.ci.j) * R + g] = acc[1] + acc2[1];
       }
       acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
       acc2[0] = acc2[1] = acc2[2] = acc2[3] = 0.f;
     }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) wc[c] = wn[c];
-    task = ntask; tg = ntg; u = nu; u_end = nu_end; j = nj;
+    it_advance(c, c.ci);
+    cslot = cslot + 1 == GV_D ? 0 : cslot + 1;
+    pslot = pslot + 1 == GV_D ? 0 : pslot + 1;
   }
+  cp_async_wait<0>();
+  GV_TRACE(3);
   __syncthreads();
+  GV_TRACE(4);
 
   // ---- epilogue: fixed-order sum over the K-slices
-  const int nrows = p.n1 - p.n0;
-  if constexpr (EPI == GEMV_OUT_SWIGLU_BF16) {
+  if (epi == GEMV_OUT_SWIGLU_BF16) {
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
-    for (int i = tid; i < (nrows / 2) * R; i += GV_THREADS) {
+    for (int i = tid; i < (nrows / 2) * R; i += nthreads) {
       const int pr = i / R, r = i - pr * R;
       float gsum = 0.f, usum = 0.f;
       for (int s = 0; s < p.ks; ++s) {
@@ -211,24 +328,108 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvArgs a) {
       out[(size_t)r * a.ld_out + (p.n0 >> 1) + pr] = __float2bfloat16_rn(h);
     }
   } else {
-    for (int i = tid; i < nrows * R; i += GV_THREADS) {
+    for (int i = tid; i < nrows * R; i += nthreads) {
       const int row = i / R, r = i - row * R;
       float s = 0.f;
       for (int q = 0; q < p.ks; ++q) s += part[((size_t)row * p.ks + q) * R + r];
+      GV_TRACE(7);
       float* o = a.out_f32 + (size_t)r * a.ld_out + p.n0 + row;
-      if constexpr (EPI == GEMV_OUT_ADD_RESID) *o += s; else *o = s;
+      if (epi == GEMV_OUT_ADD_RESID) *o = (i < nthreads ? resid_old : __ldcg(o)) + s;
+      else *o = s;
     }
   }
 }
 
-template <int R, int PRO, int EPI>
-static cudaError_t launch_r(const GemvArgs& a, int grid, size_t smem, bool pdl, cudaStream_t stream) {
-  auto kern = gemv_kernel<R, PRO, EPI>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int R>
+__global__ void __launch_bounds__(GV_MAX_WARPS * 32, 1) gemv_kernel(const GemvChain ch) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ float red[33];
+  __shared__ int4 task_tab[GV_MAX_TASKS];
+  GemvCtx c;
+  c.task_tab = task_tab;
+  c.nwarps = blockDim.x >> 5;
+  c.g = (threadIdx.x & 31) >> 2;
+  c.t = threadIdx.x & 3;
+  c.my_ring = smem_u32(smem) + (uint32_t)(threadIdx.x >> 5) * GV_D * GV_STEP_BYTES + (uint32_t)(threadIdx.x & 31) * 16;
+
+  unsigned long long* trace = ch.trace;
+  {
+    const int ph = 0;
+    GV_TRACE(0);
+    if (trace && threadIdx.x == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      trace[((size_t)blockIdx.x * 4 + 0) * 8 + 6] = smid;
+    }
+  }
+  phase_begin(ch.ph[0], c);  // weights do not depend on the previous kernel: request before the PDL wait
+  pdl_wait();
+  pdl_launch_dependents();
+#pragma unroll 1
+  for (int ph = 0; ph < ch.n; ++ph) {
+    const GemvArgs& a = ch.ph[ph];
+    GV_TRACE(1);
+    phase_rest<R>(a, c, smem, red, trace, ph);
+    GV_TRACE(5);
+    if (ph + 1 < ch.n) {
+      grid_arrive(ch.barrier + ph);
+      phase_begin(ch.ph[ph + 1], c);  // the next projection's weights start flowing while we wait for the other CTAs
+      grid_wait(ch.barrier + ph, gridDim.x);
+    }
+  }
+}
+
+static size_t gemv_smem(const GemvArgs& a, int grid, int nwarps) {
+  const int pairs = a.N / 2;
+  const int nrows_max = 2 * ((pairs + grid - 1) / grid) + 2;
+  const size_t xbytes = (size_t)a.R * (a.K + GV_XPAD) * 2;
+  const size_t part = (size_t)(32 * nwarps + 2 * nrows_max + 64) * a.R * 4;  // >= rows*ks of any CTA
+  return (size_t)nwarps * GV_D * GV_STEP_BYTES + xbytes + part;
+}
+
+cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaStream_t stream) {
+  if (ch.n < 1 || ch.n > 4) return cudaErrorInvalidValue;
+  const int R = ch.ph[0].R;
+  int grid = num_sms;
+  for (int i = 0; i < ch.n; ++i) {
+    const GemvArgs& a = ch.ph[i];
+    if (a.R != R || a.R < 1 || a.R > 8 || (a.K % 8) != 0 || (a.N % 2) != 0) return cudaErrorInvalidValue;
+    if (a.x_resid && a.epilogue == GEMV_OUT_ADD_RESID) return cudaErrorInvalidValue;
+    if (a.N / 2 < grid) grid = a.N / 2;
+  }
+  if (ch.n > 1 && (!ch.barrier || grid > num_sms)) return cudaErrorInvalidValue;
+  // one CTA per SM; as many warps (each with its private 3-step ring) as shared memory allows next to x
+  int nwarps = GV_MAX_WARPS;
+  if (const char* ev = getenv("VDD_GV_WARPS")) {  // tuning knob
+    const int w = atoi(ev);
+    if (w >= 1 && w <= GV_MAX_WARPS) nwarps = w;
+  }
+  size_t smem = 0;
+  for (; nwarps >= 1; nwarps -= (nwarps > 4 ? 2 : 1)) {
+    smem = 0;
+    for (int i = 0; i < ch.n; ++i) {
+      const size_t s = gemv_smem(ch.ph[i], grid, nwarps);
+      smem = s > smem ? s : smem;
+    }
+    if (smem <= (size_t)GV_SMEM_BUDGET) break;
+  }
+  if (nwarps < 1) return cudaErrorInvalidValue;
+  void (*kern)(const GemvChain) = nullptr;
+  switch (R) {
+    case 1: kern = gemv_kernel<1>; break;
+    case 2: kern = gemv_kernel<2>; break;
+    case 3: kern = gemv_kernel<3>; break;
+    case 4: kern = gemv_kernel<4>; break;
+    case 5: kern = gemv_kernel<5>; break;
+    case 6: kern = gemv_kernel<6>; break;
+    case 7: kern = gemv_kernel<7>; break;
+    case 8: kern = gemv_kernel<8>; break;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GV_SMEM_BUDGET);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GV_THREADS);
+  cfg.blockDim = dim3(nwarps * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -236,46 +437,14 @@ static cudaError_t launch_r(const GemvArgs& a, int grid, size_t smem, bool pdl, 
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, a);
-}
-
-template <int R>
-static cudaError_t launch_pe(const GemvArgs& a, int pro, int grid, size_t smem, bool pdl, cudaStream_t s) {
-  if (pro == GEMV_X_RMSNORM) {
-    if (a.epilogue == GEMV_OUT_F32) return launch_r<R, GEMV_X_RMSNORM, GEMV_OUT_F32>(a, grid, smem, pdl, s);
-    if (a.epilogue == GEMV_OUT_SWIGLU_BF16) return launch_r<R, GEMV_X_RMSNORM, GEMV_OUT_SWIGLU_BF16>(a, grid, smem, pdl, s);
-  } else {
-    if (a.epilogue == GEMV_OUT_F32) return launch_r<R, GEMV_X_BF16, GEMV_OUT_F32>(a, grid, smem, pdl, s);
-    if (a.epilogue == GEMV_OUT_ADD_RESID) return launch_r<R, GEMV_X_BF16, GEMV_OUT_ADD_RESID>(a, grid, smem, pdl, s);
-    if (a.epilogue == GEMV_OUT_SWIGLU_BF16) return launch_r<R, GEMV_X_BF16, GEMV_OUT_SWIGLU_BF16>(a, grid, smem, pdl, s);
-  }
-  return cudaErrorInvalidValue;
+  return cudaLaunchKernelEx(&cfg, kern, ch);
 }
 
 cudaError_t launch_gemv(const GemvArgs& a, int num_sms, bool pdl, cudaStream_t stream) {
-  if (a.R < 1 || a.R > 8 || (a.K % 8) != 0 || (a.N % 2) != 0) return cudaErrorInvalidValue;
-  const int pro = a.x_resid ? GEMV_X_RMSNORM : GEMV_X_BF16;
-  // two CTAs per SM when x fits twice, else one
-  const size_t xbytes = (size_t)a.R * (a.K + GV_XPAD) * 2;
-  int per_sm = xbytes <= 100 * 1024 ? 2 : 1;
-  int grid = num_sms * per_sm;
-  const int pairs = a.N / 2;
-  if (grid > pairs) grid = pairs;
-  const int nrows_max = 2 * ((pairs + grid - 1) / grid) + 2;
-  const size_t part = (size_t)(4 * GV_WARPS * GV_RG + 2 * nrows_max + 64) * a.R * 4;  // >= rows*ks of any CTA
-  const size_t smem = xbytes + part;
-  if (smem > 220 * 1024) return cudaErrorInvalidValue;
-  switch (a.R) {
-    case 1: return launch_pe<1>(a, pro, grid, smem, pdl, stream);
-    case 2: return launch_pe<2>(a, pro, grid, smem, pdl, stream);
-    case 3: return launch_pe<3>(a, pro, grid, smem, pdl, stream);
-    case 4: return launch_pe<4>(a, pro, grid, smem, pdl, stream);
-    case 5: return launch_pe<5>(a, pro, grid, smem, pdl, stream);
-    case 6: return launch_pe<6>(a, pro, grid, smem, pdl, stream);
-    case 7: return launch_pe<7>(a, pro, grid, smem, pdl, stream);
-    case 8: return launch_pe<8>(a, pro, grid, smem, pdl, stream);
-  }
-  return cudaErrorInvalidValue;
+  GemvChain ch{};
+  ch.ph[0] = a;
+  ch.n = 1;
+  return launch_gemv_chain(ch, num_sms, pdl, stream);
 }
 
 }  // namespace vdd

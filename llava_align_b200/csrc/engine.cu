@@ -97,7 +97,7 @@ struct vdd_engine {
   vdd_config c;
   int D = 128, heads_l = 0, Hl = 0, Il = 0, Vl = 0, NP = 0, Kpad = 0, VD = 64;
   int num_sms = 148;
-  bool use_pdl = true, use_graph = true;
+  bool use_pdl = true, use_graph = true, use_fused = true;
   // weights
   void* arena = nullptr;
   size_t arena_bytes = 0;
@@ -118,6 +118,8 @@ struct vdd_engine {
           *d_unfinished = nullptr, *d_counters = nullptr;
   int64_t *d_kv_off = nullptr, *d_head_stride = nullptr, *d_tokens = nullptr, *d_seq_out = nullptr;
   SampleArgs* d_sargs = nullptr;
+  unsigned long long* d_trace = nullptr;  // VDD_TRACE=1: time stamps of the middle layer's fused chain
+  unsigned* d_bar = nullptr;  // grid-barrier counters of the fused projection chains, [layers + 2][4]
   bool prefilled = false;
   int image_B = 0;
   // decode buffers (views into dec_f32 / dec_bf16)
@@ -194,6 +196,8 @@ extern "C" int vdd_create(const vdd_config* cfg, vdd_engine** out) {
   cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev);
   e->use_pdl = getenv("VDD_NO_PDL") == nullptr;
   e->use_graph = getenv("VDD_NO_GRAPH") == nullptr;
+  e->use_fused = getenv("VDD_NO_FUSED") == nullptr;
+  if (getenv("VDD_TRACE")) cudaMalloc(&e->d_trace, (size_t)256 * 4 * 8 * 8);
 
   const int64_t H = c.hidden_size, VH = c.v_hidden, VI = c.v_intermediate;
   std::vector<std::pair<std::string, size_t>> order;
@@ -594,7 +598,7 @@ extern "C" int vdd_prefill(vdd_engine* e, const int64_t* ids, int B, int T, int 
                  o_cap = carve((size_t)R * 4), o_pos = carve((size_t)R * 4), o_last = carve((size_t)R * 4), o_len = carve((size_t)R * 4),
                  o_q0 = carve((size_t)R * 4), o_step = carve(256), o_unf = carve((size_t)B * 4), o_cnt = carve((size_t)R * e->heads_l * 4),
                  o_off = carve((size_t)R * 8), o_hs = carve((size_t)R * 8), o_tokens = carve((size_t)B * 8),
-                 o_seq = carve((size_t)B * max_new * 8), o_sa = carve(sizeof(SampleArgs));
+                 o_seq = carve((size_t)B * max_new * 8), o_sa = carve(sizeof(SampleArgs)), o_bar = carve((size_t)(L + 2) * 4 * 4);
     RC(ensure(e, e->meta, o));
     char* b = (char*)e->meta.p;
     e->d_tok = (int32_t*)(b + o_tok); e->d_img_row = (int32_t*)(b + o_img); e->d_row_seq = (int32_t*)(b + o_rs);
@@ -602,7 +606,7 @@ extern "C" int vdd_prefill(vdd_engine* e, const int64_t* ids, int B, int T, int 
     e->d_last_rows = (int32_t*)(b + o_last); e->d_seqlen = (int32_t*)(b + o_len); e->d_q_row0 = (int32_t*)(b + o_q0);
     e->d_step = (int32_t*)(b + o_step); e->d_unfinished = (int32_t*)(b + o_unf); e->d_counters = (int32_t*)(b + o_cnt);
     e->d_kv_off = (int64_t*)(b + o_off); e->d_head_stride = (int64_t*)(b + o_hs); e->d_tokens = (int64_t*)(b + o_tokens);
-    e->d_seq_out = (int64_t*)(b + o_seq); e->d_sargs = (SampleArgs*)(b + o_sa);
+    e->d_seq_out = (int64_t*)(b + o_seq); e->d_sargs = (SampleArgs*)(b + o_sa); e->d_bar = (unsigned*)(b + o_bar);
   }
   auto up = [&](void* d, const void* h, size_t n) { return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st); };
   CK(up(e->d_tok, tok.data(), (size_t)Mtot * 4));
@@ -691,49 +695,72 @@ static int tp_gather_logits(vdd_engine* e, cudaStream_t st) {
   return VDD_OK;
 }
 
-static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_t st) {
+static GemvArgs gv_args(const void* w, const void* x_bf16, const float* x_resid, const void* norm_w, float eps, int R, int N, int K,
+                        int epi, float* of32, void* obf16, int64_t ld) {
+  GemvArgs g{};
+  g.w = w; g.x_bf16 = x_bf16; g.x_resid = x_resid; g.norm_w = norm_w; g.eps = eps; g.R = R; g.N = N; g.K = K;
+  g.epilogue = epi; g.out_f32 = of32; g.out_bf16 = obf16; g.ld_out = ld;
+  return g;
+}
+
+static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_t st, bool projections_only = false) {
   const vdd_config& c = e->c;
   const int H = c.hidden_size, L = c.num_layers, Hl = e->Hl, Il = e->Il, R = e->R;
   const bool pdl = e->use_pdl;
   const bool tp = c.tp_size > 1;
-  LK(e, launch_decode_embed(e->embed, tokens, e->resid_d, e->B, e->S, H, st));
+  const bool fused = R <= 8 && !tp && e->use_fused;  // o -> gate_up -> down -> next qkv in one launch per layer
   __nv_bfloat16* kbase = (__nv_bfloat16*)e->kv.p;
+  float* lg = tp ? (float*)e->logits_tp.p : (float*)e->logits.p;
+  auto qkv_args = [&](int l) {
+    return gv_args(e->lw[l].wqkv, nullptr, e->resid_d, e->lw[l].ln1, c.rms_eps, R, 3 * Hl, H, GEMV_OUT_F32, e->qkv_d, nullptr, 3 * Hl);
+  };
+  auto head_args = [&]() {
+    return gv_args(e->lm_head, nullptr, e->resid_d, e->final_norm, c.rms_eps, R, e->Vl, H, GEMV_OUT_F32, lg, nullptr, e->Vl);
+  };
+  if (fused) CK(cudaMemsetAsync(e->d_bar, 0, (size_t)(L + 2) * 4 * 4, st));
+  if (!projections_only) LK(e, launch_decode_embed(e->embed, tokens, e->resid_d, e->B, e->S, H, st));
+  if (fused) LK(e, launch_gemv(qkv_args(0), e->num_sms, pdl, st));
   for (int l = 0; l < L; ++l) {
     const LayerW& w = e->lw[l];
-    if (R <= 8) {
-      GemvArgs g{};
-      g.w = w.wqkv; g.x_resid = e->resid_d; g.norm_w = w.ln1; g.eps = c.rms_eps; g.R = R; g.N = 3 * Hl; g.K = H;
-      g.epilogue = GEMV_OUT_F32; g.out_f32 = e->qkv_d; g.ld_out = 3 * Hl;
-      LK(e, launch_gemv(g, e->num_sms, pdl, st));
-    } else {
-      LK(e, launch_rmsnorm_bf16(e->resid_d, w.ln1, c.rms_eps, e->xn_d, R, H, nullptr, st));
-      RC(do_gemm(e, e->xn_d, w.wqkv, R, 3 * Hl, H, GEMM_OUT_F32, nullptr, nullptr, e->qkv_d, nullptr, 3 * Hl, st));
+    if (!fused) {
+      if (R <= 8) {
+        LK(e, launch_gemv(qkv_args(l), e->num_sms, pdl, st));
+      } else {
+        LK(e, launch_rmsnorm_bf16(e->resid_d, w.ln1, c.rms_eps, e->xn_d, R, H, nullptr, st));
+        RC(do_gemm(e, e->xn_d, w.wqkv, R, 3 * Hl, H, GEMM_OUT_F32, nullptr, nullptr, e->qkv_d, nullptr, 3 * Hl, st));
+      }
     }
     DecodeAttnArgs da{};
     da.qkv = e->qkv_d; da.kcache = kbase + (size_t)l * e->kv_layer_stride; da.vcache = kbase + (size_t)(L + l) * e->kv_layer_stride;
     da.kv_off = e->d_kv_off; da.kv_cap = e->d_kv_cap; da.pos = e->d_pos; da.rope_cos = e->rope_cos; da.rope_sin = e->rope_sin;
     da.out_bf16 = e->attn_d; da.part_o = e->part_o; da.part_ml = e->part_ml; da.counters = e->d_counters;
     da.R = R; da.heads = e->heads_l; da.max_splits = e->max_splits; da.scale = 0.08838834764831845f;
-    LK(e, launch_decode_attn(da, st));
+    if (!projections_only) LK(e, launch_decode_attn(da, st));
+    if (fused) {
+      GemvChain ch{};
+      ch.ph[0] = gv_args(w.wo, e->attn_d, nullptr, nullptr, 0.f, R, H, Hl, GEMV_OUT_ADD_RESID, e->resid_d, nullptr, H);
+      ch.ph[1] = gv_args(w.wgu, nullptr, e->resid_d, w.ln2, c.rms_eps, R, 2 * Il, H, GEMV_OUT_SWIGLU_BF16, nullptr, e->h_d, Il);
+      ch.ph[2] = gv_args(w.wdown, e->h_d, nullptr, nullptr, 0.f, R, H, Il, GEMV_OUT_ADD_RESID, e->resid_d, nullptr, H);
+      ch.ph[3] = l + 1 < L ? qkv_args(l + 1) : head_args();
+      ch.n = 4;
+      ch.barrier = e->d_bar + (size_t)l * 4;
+      ch.trace = (l == L / 2) ? e->d_trace : nullptr;
+      LK(e, launch_gemv_chain(ch, e->num_sms, pdl, st));
+      continue;
+    }
     float* o_dst = tp ? (float*)e->tp_tmp.p : e->resid_d;
     const int o_mode_v = tp ? GEMV_OUT_F32 : GEMV_OUT_ADD_RESID;
     const int o_mode_m = tp ? GEMM_OUT_F32 : GEMM_OUT_ADD_F32;
     if (R <= 8) {
-      GemvArgs g{};
-      g.w = w.wo; g.x_bf16 = e->attn_d; g.R = R; g.N = H; g.K = Hl; g.epilogue = o_mode_v; g.out_f32 = o_dst; g.ld_out = H;
-      LK(e, launch_gemv(g, e->num_sms, pdl, st));
+      LK(e, launch_gemv(gv_args(w.wo, e->attn_d, nullptr, nullptr, 0.f, R, H, Hl, o_mode_v, o_dst, nullptr, H), e->num_sms, pdl, st));
     } else {
       RC(do_gemm(e, e->attn_d, w.wo, R, H, Hl, o_mode_m, nullptr, nullptr, o_dst, nullptr, H, st));
     }
     if (tp) RC(tp_allreduce_add(e, o_dst, e->resid_d, (int64_t)R * H, st));
     if (R <= 8) {
-      GemvArgs g{};
-      g.w = w.wgu; g.x_resid = e->resid_d; g.norm_w = w.ln2; g.eps = c.rms_eps; g.R = R; g.N = 2 * Il; g.K = H;
-      g.epilogue = GEMV_OUT_SWIGLU_BF16; g.out_bf16 = e->h_d; g.ld_out = Il;
-      LK(e, launch_gemv(g, e->num_sms, pdl, st));
-      GemvArgs d{};
-      d.w = w.wdown; d.x_bf16 = e->h_d; d.R = R; d.N = H; d.K = Il; d.epilogue = o_mode_v; d.out_f32 = o_dst; d.ld_out = H;
-      LK(e, launch_gemv(d, e->num_sms, pdl, st));
+      LK(e, launch_gemv(gv_args(w.wgu, nullptr, e->resid_d, w.ln2, c.rms_eps, R, 2 * Il, H, GEMV_OUT_SWIGLU_BF16, nullptr, e->h_d, Il),
+                        e->num_sms, pdl, st));
+      LK(e, launch_gemv(gv_args(w.wdown, e->h_d, nullptr, nullptr, 0.f, R, H, Il, o_mode_v, o_dst, nullptr, H), e->num_sms, pdl, st));
     } else {
       LK(e, launch_rmsnorm_bf16(e->resid_d, w.ln2, c.rms_eps, e->xn_d, R, H, nullptr, st));
       RC(do_gemm(e, e->xn_d, w.wgu, R, 2 * Il, H, GEMM_OUT_SWIGLU, nullptr, nullptr, nullptr, e->h_d, Il, st));
@@ -741,15 +768,13 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     }
     if (tp) RC(tp_allreduce_add(e, o_dst, e->resid_d, (int64_t)R * H, st));
   }
-  float* lg = tp ? (float*)e->logits_tp.p : (float*)e->logits.p;
-  if (R <= 8) {
-    GemvArgs g{};
-    g.w = e->lm_head; g.x_resid = e->resid_d; g.norm_w = e->final_norm; g.eps = c.rms_eps; g.R = R; g.N = e->Vl; g.K = H;
-    g.epilogue = GEMV_OUT_F32; g.out_f32 = lg; g.ld_out = e->Vl;
-    LK(e, launch_gemv(g, e->num_sms, pdl, st));
-  } else {
-    LK(e, launch_rmsnorm_bf16(e->resid_d, e->final_norm, c.rms_eps, e->xn_d, R, H, nullptr, st));
-    RC(do_gemm(e, e->xn_d, e->lm_head, R, e->Vl, H, GEMM_OUT_F32, nullptr, nullptr, lg, nullptr, e->Vl, st));
+  if (!fused) {
+    if (R <= 8) {
+      LK(e, launch_gemv(head_args(), e->num_sms, pdl, st));
+    } else {
+      LK(e, launch_rmsnorm_bf16(e->resid_d, e->final_norm, c.rms_eps, e->xn_d, R, H, nullptr, st));
+      RC(do_gemm(e, e->xn_d, e->lm_head, R, e->Vl, H, GEMM_OUT_F32, nullptr, nullptr, lg, nullptr, e->Vl, st));
+    }
   }
   if (tp) RC(tp_gather_logits(e, st));
   return VDD_OK;
@@ -847,7 +872,7 @@ extern "C" int vdd_generate(vdd_engine* e, const int64_t* ids, int B, int T, con
 
   int steps = 1;
   if (max_new > 1) {
-    const uint64_t key = ((uint64_t)B << 40) ^ ((uint64_t)S << 32) ^ ((uint64_t)e->max_splits << 16) ^ (uint64_t)(e->use_pdl ? 1 : 0) ^
+    const uint64_t key = ((uint64_t)B << 40) ^ ((uint64_t)S << 32) ^ ((uint64_t)e->max_splits << 16) ^ (uint64_t)(e->use_pdl ? 1 : 0) ^ (uint64_t)(e->use_fused ? 2 : 0) ^
                          ((uint64_t)(uintptr_t)e->kv.p << 1) ^ (uint64_t)(uintptr_t)e->logits.p ^ ((uint64_t)e->kv_layer_stride << 3);
     int per_step_launches = 0;
     const bool graph = e->use_graph && st != nullptr;  // the legacy default stream cannot be captured
@@ -918,6 +943,11 @@ extern "C" int vdd_generate(vdd_engine* e, const int64_t* ids, int B, int T, con
   return VDD_OK;
 }
 
+extern "C" int vdd_debug_trace(vdd_engine* e, unsigned long long* out_host, int n) {
+  if (!e || !e->d_trace) return fail(VDD_ERR_STATE, "set VDD_TRACE=1 before vdd_create");
+  CK(cudaMemcpy(out_host, e->d_trace, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return VDD_OK;
+}
 extern "C" int64_t vdd_launch_count(vdd_engine* e, int reset) {
   if (!e) return 0;
   const int64_t n = e->launches;
@@ -937,31 +967,7 @@ extern "C" int vdd_last_timings(vdd_engine* e, float* v, float* p, float* d) {
 extern "C" int vdd_bench_projection_chain(vdd_engine* e, void* stream_v) {
   if (!e || !e->prefilled) return fail(VDD_ERR_STATE, "vdd_prefill must run first");
   if (e->R > 8) return fail(VDD_ERR_UNSUPPORTED, "projection chain is the R<=8 GEMV path");
-  cudaStream_t st = (cudaStream_t)stream_v;
-  const vdd_config& c = e->c;
-  const int H = c.hidden_size, Hl = e->Hl, Il = e->Il, R = e->R;
-  for (int l = 0; l < c.num_layers; ++l) {
-    const LayerW& w = e->lw[l];
-    GemvArgs g{};
-    g.w = w.wqkv; g.x_resid = e->resid_d; g.norm_w = w.ln1; g.eps = c.rms_eps; g.R = R; g.N = 3 * Hl; g.K = H;
-    g.epilogue = GEMV_OUT_F32; g.out_f32 = e->qkv_d; g.ld_out = 3 * Hl;
-    LK(e, launch_gemv(g, e->num_sms, e->use_pdl, st));
-    GemvArgs o{};
-    o.w = w.wo; o.x_bf16 = e->attn_d; o.R = R; o.N = H; o.K = Hl; o.epilogue = GEMV_OUT_F32; o.out_f32 = (float*)e->qkv_d; o.ld_out = H;
-    LK(e, launch_gemv(o, e->num_sms, e->use_pdl, st));
-    GemvArgs u{};
-    u.w = w.wgu; u.x_resid = e->resid_d; u.norm_w = w.ln2; u.eps = c.rms_eps; u.R = R; u.N = 2 * Il; u.K = H;
-    u.epilogue = GEMV_OUT_SWIGLU_BF16; u.out_bf16 = e->h_d; u.ld_out = Il;
-    LK(e, launch_gemv(u, e->num_sms, e->use_pdl, st));
-    GemvArgs d{};
-    d.w = w.wdown; d.x_bf16 = e->h_d; d.R = R; d.N = H; d.K = Il; d.epilogue = GEMV_OUT_F32; d.out_f32 = (float*)e->qkv_d; d.ld_out = H;
-    LK(e, launch_gemv(d, e->num_sms, e->use_pdl, st));
-  }
-  GemvArgs g{};
-  g.w = e->lm_head; g.x_resid = e->resid_d; g.norm_w = e->final_norm; g.eps = c.rms_eps; g.R = R; g.N = e->Vl; g.K = H;
-  g.epilogue = GEMV_OUT_F32; g.out_f32 = (float*)(c.tp_size > 1 ? e->logits_tp.p : e->logits.p); g.ld_out = e->Vl;
-  LK(e, launch_gemv(g, e->num_sms, e->use_pdl, st));
-  return VDD_OK;
+  return decode_step_enqueue(e, nullptr, (cudaStream_t)stream_v, true);
 }
 
 // ------------------------------------------------------------------------------------------------ TP

@@ -36,6 +36,14 @@ struct GemvArgs {
   int64_t ld_out;       // row pitch of the output in elements
 };
 cudaError_t launch_gemv(const GemvArgs& a, int num_sms, bool pdl, cudaStream_t stream);
+// up to four projections in ONE launch, separated by grid barriers (barrier: n-1 counters, zero on entry)
+struct GemvChain {
+  GemvArgs ph[4];
+  int n;
+  unsigned* barrier;
+  unsigned long long* trace;  // debug: [grid][4 phases][8 slots] globaltimer stamps of thread 0, or null
+};
+cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaStream_t stream);
 
 // ---------------------------------------------------------------- tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T
 enum GemmEpilogue {
