@@ -34,6 +34,9 @@ def parse():
     ap.add_argument("--new-tokens", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--parallel", default="dp", choices=["dp", "tp"],
+                    help="N>1: dp = one independent request stream per GPU (how the reference scales: one process per GPU, "
+                         "scripts/pope/run_dataset.sh:14-32), no collective, weak scaling; tp = tensor parallel over NCCL, strong scaling")
     ap.add_argument("--profile", action="store_true", help="under ncu: the device-resident leg only, no extra launches")
     return ap.parse_args()
 
@@ -137,12 +140,14 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(a, cfg, n):
+def workload_config(a, cfg, n, mode="dp"):
     return {"workload": f"BASELINE.json configs[1]: {cfg.name} bf16 random-init, batch {a.batch}, 1 synthetic "
                         f"{cfg.image_size}px image, {a.prompt_len}-token prompt, {a.new_tokens} new tokens, use_dd+use_dd_unk "
                         f"(3 fused streams), cd_alpha=1 cd_beta=0.1, temperature-1 sampling, EOS disabled",
             "global_batch": a.batch, "new_tokens": a.new_tokens, "prompt_len": a.prompt_len, "streams": 3,
-            "parallelism": "single GPU" if n == 1 else f"tp{n} (heads/FFN/vocab split, NCCL all-reduce)",
+            "parallelism": "single GPU" if n == 1 else (
+                f"tp{n} (heads/FFN/vocab split, NCCL all-reduce after o_proj/down_proj, all-gather of the vocab shards)" if mode == "tp"
+                else f"dp{n}: {n} independent replicas, one request stream per GPU, no data-path collective"),
             "l2_policy": "inputs larger than L2: every step streams the 13.2 GB of weights (L2 = 126 MB); no flush needed"}
 
 
@@ -169,9 +174,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = by_name(a.model)
     evolve_vcd_sampling()
-    tok, model, _, _ = load_pretrained_model(f"random:{a.model}:0", None, a.model, device=str(dev), tp_size=world, tp_rank=rank)
+    tp = world if a.parallel == "tp" else 1
+    tok, model, _, _ = load_pretrained_model(f"random:{a.model}:0", None, a.model, device=str(dev), tp_size=tp,
+                                             tp_rank=rank if tp > 1 else 0)
     eng = model.engine
-    if world > 1:
+    if tp > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             idt = torch.frombuffer(bytearray(E.VddEngine.tp_unique_id()), dtype=torch.uint8).to(dev)
@@ -216,23 +223,25 @@ def main():
     dev_fn = lambda: eng.generate(ids, img_dev, True, True, params, n_new, q, None)
     ms, launches = timed(dev_fn, a.warmup, a.steps)
     tm = eng.last_timings()
-    value = B * n_new * a.steps / (ms / 1e3)
+    replicas = world if tp == 1 else 1  # dp: every rank generated its own B x n_new tokens in the (max-over-ranks) time
+    value = replicas * B * n_new * a.steps / (ms / 1e3)
     # ---- e2e: the reference-facing call with pinned host buffers (H2D pixels, D2H tokens inside)
     e2e = None
     if not a.no_e2e:
         gen_kw = dict(images=img_pinned, images_cd=None, cd_alpha=1.0, cd_beta=0.1, use_dd=True, use_dd_unk=True, do_sample=True,
                       temperature=1.0, top_p=None, top_k=None, max_new_tokens=n_new, use_cache=True, eos_token_id=None)
-        if world > 1:
+        if tp > 1:
             torch.manual_seed(4321)  # all TP ranks must draw the same variates
         e2e_fn = lambda: model.generate(ids_pinned, **gen_kw)
         ms2, _ = timed(e2e_fn, 1, a.steps)
-        e2e = {"value": B * n_new * a.steps / (ms2 / 1e3), "unit": "tokens/s",
-               "h2d_bytes_per_step": int(img.numel() * 2 + ids.numel() * 8), "d2h_bytes_per_step": int(B * n_new * 8),
+        e2e = {"value": replicas * B * n_new * a.steps / (ms2 / 1e3), "unit": "tokens/s",
+               "h2d_bytes_per_step": int(replicas * (img.numel() * 2 + ids.numel() * 8)),
+               "d2h_bytes_per_step": int(replicas * B * n_new * 8),
                "ms_per_step": ms2 / a.steps}
     clocks = sampler.stop() if sampler else None
 
     # ---- roofline of the dominant kernel (gemv_kernel: every projection of the decode step), timed live with CUDA events
-    proj_bytes, kv_tok = algorithmic_bytes(cfg, world)
+    proj_bytes, kv_tok = algorithmic_bytes(cfg, tp)
     L = cfg.num_hidden_layers
     n_proj = 4 * L + 1
     lib = _lib.load()
@@ -282,9 +291,10 @@ def main():
                "phases": {k: r[k] for k in ("vision_s", "prefill_s", "decode_s_per_token")}}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic", "config": workload_config(a, cfg, world), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": int(launches), "roofline": roofline, "decode_step": decode, "cpu_baseline": cpu}
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(a, cfg, world, a.parallel),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * replicas, "roofline": roofline, "decode_step": decode,
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
