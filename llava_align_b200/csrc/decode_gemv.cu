@@ -59,7 +59,10 @@ __host__ __device__ __forceinline__ GemvPlan make_plan(int N, int K, int cta, in
   const int nrows = p.n1 - p.n0;
   p.ngroups = (nrows + GV_RG - 1) / GV_RG;
   p.nunits = (K + GV_UNIT - 1) / GV_UNIT;
-  int ks = p.ngroups > 0 ? (4 * nwarps + p.ngroups - 1) / p.ngroups : 1;
+  // the K-split must not depend on the warp count (which follows R through the shared-memory budget): a row's
+  // result has to be bit-identical whatever other rows are fused beside it
+  (void)nwarps;
+  int ks = p.ngroups > 0 ? (4 * GV_MAX_WARPS + p.ngroups - 1) / p.ngroups : 1;
   const int ksmax = p.nunits / 2 > 1 ? p.nunits / 2 : 1;
   ks = ks < 1 ? 1 : (ks > ksmax ? ksmax : ks);
   p.ks = ks;
@@ -383,7 +386,7 @@ static size_t gemv_smem(const GemvArgs& a, int grid, int nwarps) {
   const int pairs = a.N / 2;
   const int nrows_max = 2 * ((pairs + grid - 1) / grid) + 2;
   const size_t xbytes = (size_t)a.R * (a.K + GV_XPAD) * 2;
-  const size_t part = (size_t)(32 * nwarps + 2 * nrows_max + 64) * a.R * 4;  // >= rows*ks of any CTA
+  const size_t part = (size_t)(32 * GV_MAX_WARPS + 2 * nrows_max + 64) * a.R * 4;  // >= rows*ks of any CTA
   return (size_t)nwarps * GV_D * GV_STEP_BYTES + xbytes + part;
 }
 

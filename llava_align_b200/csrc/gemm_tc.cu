@@ -24,7 +24,7 @@ constexpr int GM_STAGE_BYTES = (GM_BM + GM_BN) * GM_BK * 2;  // 32 KB
 constexpr int GM_SMEM = GM_STAGES * GM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GemmEpi {
-  int M, N, K, mode;
+  int M, N, K, mode, splits;
   const __nv_bfloat16* bias;
   const int32_t* row_map;
   float* out_f32;
@@ -47,7 +47,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * GM_BN, m0 = blockIdx.y * GM_BM;
-  const int nkb = (ep.K + GM_BK - 1) / GM_BK;
+  // split-K (skinny decode GEMMs whose N/128 tiles cannot fill 148 SMs): this CTA owns k-blocks [kb0, kb1)
+  const int nkb_all = (ep.K + GM_BK - 1) / GM_BK;
+  const int kb0 = (int)(((long long)blockIdx.z * nkb_all) / ep.splits), kb1 = (int)(((long long)(blockIdx.z + 1) * nkb_all) / ep.splits);
+  const int nkb = kb1 - kb0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -74,8 +77,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         unsigned char* sa = smem + s * GM_STAGE_BYTES;
         unsigned char* sb = sa + GM_BM * GM_BK * 2;
         mbar_arrive_expect_tx(&full_bar[s], GM_STAGE_BYTES);
-        tma_load_2d(sa, &tmap_a, &full_bar[s], kb * GM_BK, m0);
-        tma_load_2d(sb, &tmap_b, &full_bar[s], kb * GM_BK, n0);
+        tma_load_2d(sa, &tmap_a, &full_bar[s], (kb0 + kb) * GM_BK, m0);
+        tma_load_2d(sb, &tmap_b, &full_bar[s], (kb0 + kb) * GM_BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -114,7 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
-      if (ep.bias) {
+      if (ep.bias && blockIdx.z == 0) {
         const uint4 b0 = *reinterpret_cast<const uint4*>(ep.bias + col);
         const uint4 b1 = *reinterpret_cast<const uint4*>(ep.bias + col + 8);
         const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -126,6 +129,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 t = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          if (ep.mode == GEMM_OUT_ADD_F32 && ep.splits > 1) {  // K-slices of one tile meet in the residual
+            float* of = reinterpret_cast<float*>(o + i);
+            atomicAdd(of, t.x); atomicAdd(of + 1, t.y); atomicAdd(of + 2, t.z); atomicAdd(of + 3, t.w);
+            continue;
+          }
           if (ep.mode == GEMM_OUT_ADD_F32) {
             const float4 old = o[i];
             t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
@@ -219,6 +227,15 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
   ep.ldc = a.ldc;
   dim3 grid((a.N + GM_BN - 1) / GM_BN, (a.M + GM_BM - 1) / GM_BM);
+  ep.splits = 1;
+  if (a.epilogue == GEMM_OUT_ADD_F32 && a.M <= GM_BM) {  // decode-sized residual GEMM: spread K over the idle SMs
+    const int tiles = grid.x * grid.y, nkb = (a.K + GM_BK - 1) / GM_BK;
+    int sp = 148 / (tiles > 0 ? tiles : 1);
+    if (sp > nkb / 4) sp = nkb / 4;
+    if (sp > 16) sp = 16;
+    if (sp > 1) ep.splits = sp;
+  }
+  grid.z = ep.splits;
   gemm_tc_kernel<<<grid, GM_THREADS, GM_SMEM, stream>>>(ta, tb, ep);
   return cudaGetLastError();
 }
