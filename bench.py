@@ -288,6 +288,31 @@ def main():
               "frac_of_peak": (step_bytes / (step_ms / 1e3) / 1e9 / peak) if step_ms > 0 else None,
               "vision_ms": tm["vision_ms"], "prefill_ms": tm["prefill_ms"]}
 
+    # ---- the second half of BASELINE.json's metric: logit-combine GB/s (K8 alone, 3 streams + q, scores not requested)
+    combine = None
+    if rank == 0 and not a.profile:
+        combine = []
+        for Bc in (1, 32, 64, 1024):
+            gl = torch.Generator(device=dev).manual_seed(Bc)
+            l = torch.randn(Bc, V, device=dev, generator=gl) * 2.5
+            u = l + torch.randn(Bc, V, device=dev, generator=gl)
+            d = l + torch.randn(Bc, V, device=dev, generator=gl)
+            qq = torch.empty(Bc, V, device=dev).exponential_(1, generator=gl)
+            for _ in range(3):
+                E.logit_combine_sample(l, u, d, 1.0, 0.1, q=qq)
+            reps_c = 50
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(reps_c):
+                E.logit_combine_sample(l, u, d, 1.0, 0.1, q=qq)
+            c1.record()
+            torch.cuda.synchronize()
+            us = 1e3 * c0.elapsed_time(c1) / reps_c
+            nbytes = Bc * V * 4 * 4 + Bc * 8
+            combine.append({"B": Bc, "us_per_launch": us, "GBps": nbytes / us / 1e3, "bytes": nbytes,
+                            "resident": "L2" if nbytes < 100e6 else "HBM (inputs larger than L2)"})
+        del l, u, d, qq
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import cpu_baseline as cb
@@ -299,7 +324,7 @@ def main():
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(a, cfg, world, a.parallel),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * replicas, "roofline": roofline, "decode_step": decode,
-                "cpu_baseline": cpu}
+                "logit_combine": combine, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

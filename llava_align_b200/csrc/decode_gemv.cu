@@ -5,11 +5,11 @@
 // here the weights are streamed ONCE for all R rows).  Algorithmic bytes = N*K*2.
 //
 // Layout: W bf16 [N, K] row-major.  Each CTA owns a contiguous band of output features; inside the CTA a warp
-// task is (8 consecutive features) x (a K-slice).  Lane (g, t) = (lane/4, lane%4) streams 16-byte pieces of weight
-// row g with cp.async (16 B, L1 bypass) into a PRIVATE shared-memory ring of 3 steps per warp: one warp step covers
-// 8 rows x 256 k (every row contributing 512 contiguous bytes), two steps (8 KB per warp, 128 KB per SM) are always in
-// flight while the third is consumed, and since a lane only ever reads back the bytes it requested itself the ring
-// needs no barrier at all -- cp.async.wait_group is the only synchronisation in the stream loop.
+// task is (8 consecutive features) x (a K-slice).  One warp step covers 8 rows x 256 k; each of its 8 cp.async
+// instructions (16 B per lane, L1 bypass) moves 512 CONTIGUOUS bytes of one weight row into a PRIVATE shared-memory
+// ring of 3 steps per warp (two steps = 8 KB per warp in flight while the third is consumed).  The ring is warp
+// private, so cp.async.wait_group + __syncwarp is the only synchronisation in the stream loop; a 16-byte-chunk XOR
+// swizzle makes the fragment reads (lane (g, t) = (lane/4, lane%4) reads row g) bank-conflict free.
 // The arithmetic runs on the tensor cores as mma.sync m16n8k16 (bf16 x bf16 -> fp32) with the ROLES SWAPPED: the R<=8
 // activation rows are the M side (rows R..15 are zero registers) and the 8 weight rows are the N side, so a lane's
 // 16-byte weight piece IS its B fragment for two MMAs and its 16-byte piece of x (bf16 in shared memory) IS the A
@@ -62,7 +62,7 @@ __host__ __device__ __forceinline__ GemvPlan make_plan(int N, int K, int cta, in
   // the K-split must not depend on the warp count (which follows R through the shared-memory budget): a row's
   // result has to be bit-identical whatever other rows are fused beside it
   (void)nwarps;
-  int ks = p.ngroups > 0 ? (4 * GV_MAX_WARPS + p.ngroups - 1) / p.ngroups : 1;
+  int ks = p.ngroups > 0 ? (8 * GV_MAX_WARPS + p.ngroups - 1) / p.ngroups : 1;
   const int ksmax = p.nunits / 2 > 1 ? p.nunits / 2 : 1;
   ks = ks < 1 ? 1 : (ks > ksmax ? ksmax : ks);
   p.ks = ks;
@@ -118,37 +118,65 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 // position of a warp inside its (task, step) sequence
 struct GemvIter {
-  int task, tg, u, u_end, j;
+  int task, tg, u, u_end, j, seq;
 };
 struct GemvCtx {
   GemvPlan p;
   GemvIter pi, ci;
   int4* task_tab;
-  uint32_t my_ring;  // shared-space address of this lane's 16 bytes in slot 0 of its warp's ring
+  int* task_next;   // shared counter: tasks are handed to warps on demand (balance does not depend on ntasks % nwarps)
+  int* task_fifo;   // [nwarps][8]: ids grabbed by a warp's request iterator, replayed by its consume iterator
+  uint32_t ring_warp;  // shared-space address of slot 0 of this warp's ring
   int nwarps, g, t;
 };
-__device__ __forceinline__ void it_open(const GemvCtx& c, GemvIter& it, int task) {
+__device__ __forceinline__ void it_load(const GemvCtx& c, GemvIter& it, int task) {
   it.task = task;
   if (task < c.p.ntasks) {
     const int4 tk = c.task_tab[task];
     it.tg = tk.x; it.u = tk.y; it.u_end = tk.z; it.j = tk.w;
   }
 }
-__device__ __forceinline__ void it_advance(const GemvCtx& c, GemvIter& it) {
-  if (++it.u >= it.u_end) it_open(c, it, it.task + c.nwarps);
+// the request iterator grabs the next task of the CTA and remembers it for the consume iterator of the same warp
+__device__ __forceinline__ void it_grab(const GemvCtx& c, GemvIter& it) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int task = 0;
+  if (lane == 0) {
+    task = atomicAdd(c.task_next, 1);
+    c.task_fifo[warp * 8 + (it.seq & 7)] = task;
+  }
+  task = __shfl_sync(0xffffffffu, task, 0);
+  it.seq++;
+  it_load(c, it, task);
 }
-// request one step (8 x 16 B per lane) into ring slot `slot`; always commits a group so the counting stays uniform
+__device__ __forceinline__ void it_replay(const GemvCtx& c, GemvIter& it) {
+  __syncwarp();
+  const int task = c.task_fifo[(threadIdx.x >> 5) * 8 + (it.seq & 7)];
+  it.seq++;
+  it_load(c, it, task);
+}
+template <bool PRODUCER>
+__device__ __forceinline__ void it_advance(const GemvCtx& c, GemvIter& it) {
+  if (++it.u >= it.u_end) {
+    if (PRODUCER) it_grab(c, it); else it_replay(c, it);
+  }
+}
+// request one step into ring slot `slot`: instruction q copies 512 CONTIGUOUS bytes of weight row q of the group (lane l
+// takes bytes [16 l, 16 l + 16)) -- the best shape HBM can be asked for.  The destination is swizzled (16-byte chunk
+// index ^ 4 on odd rows) so that the fragment reads below are bank-conflict free.  Always commits a group so the
+// counting stays uniform.
 __device__ __forceinline__ void ring_request(const GemvCtx& c, const __nv_bfloat16* W, int K, const GemvIter& it, int slot) {
   if (it.task < c.p.ntasks) {
-    int row = c.p.n0 + it.tg * GV_RG + c.g;
-    row = row < c.p.n1 ? row : c.p.n1 - 1;
-    const int k0 = it.u * GV_UNIT + c.t * 8;
-    const __nv_bfloat16* wr = W + (size_t)row * K + k0;
-    const uint32_t dst = c.my_ring + (uint32_t)slot * GV_STEP_BYTES;
+    const int lane = threadIdx.x & 31;
+    const int k0 = it.u * GV_UNIT + lane * 8;
+    const bool ok = k0 < K;  // ragged K (tensor-parallel slices): zero-fill
+    const int row0 = c.p.n0 + it.tg * GV_RG;
+    const uint32_t dst = c.ring_warp + (uint32_t)slot * GV_STEP_BYTES;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const bool ok = k0 + q * 32 < K;  // ragged K (tensor-parallel slices): zero-fill
-      cp_async16(dst + q * 512, ok ? (const void*)(wr + q * 32) : (const void*)W, ok ? 16u : 0u);
+      int row = row0 + q;
+      row = row < c.p.n1 ? row : c.p.n1 - 1;
+      const __nv_bfloat16* src = W + (size_t)row * K + k0;
+      cp_async16(dst + q * 512 + ((lane ^ ((q & 1) << 2)) << 4), ok ? (const void*)src : (const void*)W, ok ? 16u : 0u);
     }
   }
   cp_async_commit();
@@ -162,14 +190,18 @@ __device__ __forceinline__ void phase_begin(const GemvArgs& a, GemvCtx& c) {
     const int gi = i / c.p.ks, ji = i - gi * c.p.ks;
     c.task_tab[i] = make_int4(gi, (ji * c.p.nunits) / c.p.ks, ((ji + 1) * c.p.nunits) / c.p.ks, ji);
   }
+  if (tid == 0) *c.task_next = 0;
   __syncthreads();
-  it_open(c, c.pi, warp);
-  c.ci = c.pi;
+  (void)warp;
+  c.pi.seq = 0;
+  c.ci.seq = 0;
+  it_grab(c, c.pi);
+  it_replay(c, c.ci);
   const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(a.w);
 #pragma unroll
   for (int s = 0; s < GV_D - 1; ++s) {
     ring_request(c, W, a.K, c.pi, s);
-    if (c.pi.task < c.p.ntasks) it_advance(c, c.pi);
+    if (c.pi.task < c.p.ntasks) it_advance<true>(c, c.pi);
   }
 }
 
@@ -181,7 +213,7 @@ __device__ __forceinline__ void phase_rest(const GemvArgs& a, GemvCtx& c, unsign
   const int K = a.K;
   const int XS = K + GV_XPAD;  // x row stride (elements)
   const int nthreads = blockDim.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int g = c.g, t = c.t;
   const GemvPlan& p = c.p;
   const int epi = a.epilogue;
@@ -199,68 +231,68 @@ __device__ __forceinline__ void phase_rest(const GemvArgs& a, GemvCtx& c, unsign
   }
   // ---- prologue: stage x (bf16) in shared memory.  Loads go to L2 (.cg): the producer may be another CTA of this launch.
   if (a.x_resid) {
+    // RMSNorm.  The sum of squares is formed per 128-element chunk (one warp load, fixed shuffle tree) and the chunk
+    // sums are added in chunk order, so rstd -- and with it every output bit -- does not depend on how many warps the
+    // launch has (which follows R through the shared-memory budget).
     const __nv_bfloat16* nw = reinterpret_cast<const __nv_bfloat16*>(a.norm_w);
-    constexpr int PASS = R <= 3 ? 4 : (R <= 4 ? 3 : 1);  // float4 per thread per row held in registers
-    if (K <= PASS * 4 * nthreads) {
-      float4 xv[R][PASS];
-      float ss[R];
+    const int lane = tid & 31, nwarps = nthreads >> 5;
+    const int nchunks = K / 128;  // host guarantees K % 128 == 0 for this prologue
+    float* csum = part;           // [R][nchunks] scratch (part is not in use yet)
+    constexpr int MAXC = R <= 4 ? 3 : 1;
+    float4 keep[R][MAXC];
+    const bool kept = nchunks <= MAXC * nwarps;
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) {
+      const int ch = q * nwarps + warp;
+      if (ch < nchunks) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) keep[r][q] = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + ch * 128) + lane);
+      }
+    }
+    for (int ch = warp, q = 0; ch < nchunks; ch += nwarps, ++q) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        ss[r] = 0.f;
+        float4 xv;
+        if (q < MAXC) {
+          xv = keep[r][0];
 #pragma unroll
-        for (int q = 0; q < PASS; ++q) {
-          const int k = (q * nthreads + tid) * 4;
-          xv[r][q] = k < K ? __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int qq = 1; qq < MAXC; ++qq) if (q == qq) xv = keep[r][qq];
+        } else {
+          xv = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + ch * 128) + lane);
         }
+        float v = xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) csum[r * nchunks + ch] = v;
       }
+    }
+    __syncthreads();
+    float rstd[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r)
+    for (int r = 0; r < R; ++r) {
+      float tot = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) tot += csum[r * nchunks + ch];
+      rstd[r] = rsqrtf(tot / (float)K + a.eps);
+    }
+    __syncthreads();  // csum aliases part
+    for (int ch = warp, q = 0; ch < nchunks; ch += nwarps, ++q) {
+      const int k = ch * 128 + lane * 4;
+      const uint2 wv = *reinterpret_cast<const uint2*>(nw + k);
+      const float w0 = bf16lo(wv.x), w1 = bf16hi(wv.x), w2 = bf16lo(wv.y), w3 = bf16hi(wv.y);
 #pragma unroll
-        for (int q = 0; q < PASS; ++q)
-          ss[r] += xv[r][q].x * xv[r][q].x + xv[r][q].y * xv[r][q].y + xv[r][q].z * xv[r][q].z + xv[r][q].w * xv[r][q].w;
-      float rstd[R];
+      for (int r = 0; r < R; ++r) {
+        float4 xv;
+        if (kept && q < MAXC) {
+          xv = keep[r][0];
 #pragma unroll
-      for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(block_reduce<false>(ss[r], red) / (float)K + a.eps);
-#pragma unroll
-      for (int q = 0; q < PASS; ++q) {
-        const int k = (q * nthreads + tid) * 4;
-        if (k < K) {
-          const uint2 wv = *reinterpret_cast<const uint2*>(nw + k);
-          const float w0 = bf16lo(wv.x), w1 = bf16hi(wv.x), w2 = bf16lo(wv.y), w3 = bf16hi(wv.y);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            uint2 o;
-            o.x = pack_bf16(xv[r][q].x * rstd[r] * w0, xv[r][q].y * rstd[r] * w1);
-            o.y = pack_bf16(xv[r][q].z * rstd[r] * w2, xv[r][q].w * rstd[r] * w3);
-            *reinterpret_cast<uint2*>(xs + (size_t)r * XS + k) = o;
-          }
+          for (int qq = 1; qq < MAXC; ++qq) if (q == qq) xv = keep[r][qq];
+        } else {
+          xv = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k));
         }
-      }
-    } else {  // wide rows: two passes over L2
-      float ss[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) ss[r] = 0.f;
-      for (int k = tid * 4; k < K; k += nthreads * 4) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float4 xv = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k));
-          ss[r] += xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
-        }
-      }
-      float rstd[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(block_reduce<false>(ss[r], red) / (float)K + a.eps);
-      for (int k = tid * 4; k < K; k += nthreads * 4) {
-        const uint2 wv = *reinterpret_cast<const uint2*>(nw + k);
-        const float w0 = bf16lo(wv.x), w1 = bf16hi(wv.x), w2 = bf16lo(wv.y), w3 = bf16hi(wv.y);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float4 xv = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k));
-          uint2 o;
-          o.x = pack_bf16(xv.x * rstd[r] * w0, xv.y * rstd[r] * w1);
-          o.y = pack_bf16(xv.z * rstd[r] * w2, xv.w * rstd[r] * w3);
-          *reinterpret_cast<uint2*>(xs + (size_t)r * XS + k) = o;
-        }
+        uint2 o;
+        o.x = pack_bf16(xv.x * rstd[r] * w0, xv.y * rstd[r] * w1);
+        o.y = pack_bf16(xv.z * rstd[r] * w2, xv.w * rstd[r] * w3);
+        *reinterpret_cast<uint2*>(xs + (size_t)r * XS + k) = o;
       }
     }
   } else {
@@ -282,17 +314,23 @@ __device__ __forceinline__ void phase_rest(const GemvArgs& a, GemvCtx& c, unsign
   // lanes with g >= R read x row 0: their products land in accumulator rows nobody stores
   const __nv_bfloat16* xrow = xs + (size_t)(g < R ? g : 0) * XS + t * 8;
   int cslot = 0, pslot = GV_D - 1;
+  // lane (g, t) reads weight row g: logical 16-byte chunk qq*4+t of the row's 512 bytes, at its swizzled position
+  // (row parity flips bit 2 of the chunk index = the low bit of the 64-byte piece index q)
+  const uint32_t frag_off = (uint32_t)g * 512 + (uint32_t)t * 16;
+  const int godd = g & 1;
   while (c.ci.task < p.ntasks) {
+    __syncwarp();  // every lane is done reading the slot that is about to be refilled
     ring_request(c, W, K, c.pi, pslot);
-    if (c.pi.task < p.ntasks) it_advance(c, c.pi);
+    if (c.pi.task < p.ntasks) it_advance<true>(c, c.pi);
     cp_async_wait<GV_D - 1>();  // everything but the newest GV_D-1 groups has landed: the step to consume is there
+    __syncwarp();               // ... for every lane of the warp (fragments are assembled from other lanes' copies)
     {
-      const uint4* wq = reinterpret_cast<const uint4*>(ring + (size_t)(warp * GV_D + cslot) * GV_STEP_BYTES) + lane;
+      const unsigned char* wq = ring + (size_t)(warp * GV_D + cslot) * GV_STEP_BYTES + frag_off;
       const __nv_bfloat16* xp = xrow + c.ci.u * GV_UNIT;
       const bool full = (c.ci.u + 1) * GV_UNIT <= K;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const uint4 wv = wq[q * 32];
+        const uint4 wv = *reinterpret_cast<const uint4*>(wq + ((q ^ godd) << 6));
         uint4 xv = make_uint4(0u, 0u, 0u, 0u);
         if (full || c.ci.u * GV_UNIT + q * 32 + t * 8 < K) xv = *reinterpret_cast<const uint4*>(xp + q * 32);
         mma_bf16_16816(acc, xv.x, xv.y, wv.x, wv.y);
@@ -308,7 +346,7 @@ __device__ __forceinline__ void phase_rest(const GemvArgs& a, GemvCtx& c, unsign
       acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
       acc2[0] = acc2[1] = acc2[2] = acc2[3] = 0.f;
     }
-    it_advance(c, c.ci);
+    it_advance<false>(c, c.ci);
     cslot = cslot + 1 == GV_D ? 0 : cslot + 1;
     pslot = pslot + 1 == GV_D ? 0 : pslot + 1;
   }
@@ -348,12 +386,16 @@ __global__ void __launch_bounds__(GV_MAX_WARPS * 32, 1) gemv_kernel(const GemvCh
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ float red[33];
   __shared__ int4 task_tab[GV_MAX_TASKS];
+  __shared__ int task_next;
+  __shared__ int task_fifo[GV_MAX_WARPS * 8];
   GemvCtx c;
   c.task_tab = task_tab;
+  c.task_next = &task_next;
+  c.task_fifo = task_fifo;
   c.nwarps = blockDim.x >> 5;
   c.g = (threadIdx.x & 31) >> 2;
   c.t = threadIdx.x & 3;
-  c.my_ring = smem_u32(smem) + (uint32_t)(threadIdx.x >> 5) * GV_D * GV_STEP_BYTES + (uint32_t)(threadIdx.x & 31) * 16;
+  c.ring_warp = smem_u32(smem) + (uint32_t)(threadIdx.x >> 5) * GV_D * GV_STEP_BYTES;
 
   unsigned long long* trace = ch.trace;
   {
@@ -386,7 +428,7 @@ static size_t gemv_smem(const GemvArgs& a, int grid, int nwarps) {
   const int pairs = a.N / 2;
   const int nrows_max = 2 * ((pairs + grid - 1) / grid) + 2;
   const size_t xbytes = (size_t)a.R * (a.K + GV_XPAD) * 2;
-  const size_t part = (size_t)(32 * GV_MAX_WARPS + 2 * nrows_max + 64) * a.R * 4;  // >= rows*ks of any CTA
+  const size_t part = (size_t)(64 * GV_MAX_WARPS + 2 * nrows_max + 64) * a.R * 4;  // >= rows*ks of any CTA
   return (size_t)nwarps * GV_D * GV_STEP_BYTES + xbytes + part;
 }
 
@@ -397,7 +439,7 @@ cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaSt
   for (int i = 0; i < ch.n; ++i) {
     const GemvArgs& a = ch.ph[i];
     if (a.R != R || a.R < 1 || a.R > 8 || (a.K % 8) != 0 || (a.N % 2) != 0) return cudaErrorInvalidValue;
-    if (a.x_resid && a.epilogue == GEMV_OUT_ADD_RESID) return cudaErrorInvalidValue;
+    if (a.x_resid && (a.epilogue == GEMV_OUT_ADD_RESID || (a.K % 128) != 0)) return cudaErrorInvalidValue;
     if (a.N / 2 < grid) grid = a.N / 2;
   }
   if (ch.n > 1 && (!ch.barrier || grid > num_sms)) return cudaErrorInvalidValue;

@@ -241,6 +241,26 @@ cudaError_t launch_add_rows(float* dst, const float* src, int64_t n, cudaStream_
   return cudaGetLastError();
 }
 
+// split-K partials of a residual GEMM, summed in split order (deterministic) and added to the residual stream
+__global__ void reduce_splits_kernel(float* __restrict__ dst, const float* __restrict__ ws, int64_t n4, int splits) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    for (int z = 0; z < splits; ++z) {
+      const float4 b = reinterpret_cast<const float4*>(ws)[(int64_t)z * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+}
+cudaError_t launch_reduce_splits(float* dst, const float* ws, int64_t n, int splits, cudaStream_t stream) {
+  const int64_t n4 = n / 4;
+  int grid = (int)((n4 + 255) / 256);
+  if (grid > 1184) grid = 1184;
+  if (grid < 1) grid = 1;
+  reduce_splits_kernel<<<grid, 256, 0, stream>>>(dst, ws, n4, splits);
+  return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int H,
                                                        const int32_t* __restrict__ row_idx) {
   const int row = blockIdx.x;

@@ -109,7 +109,7 @@ struct vdd_engine {
   void *patch_w, *cls, *vpos, *preln_w, *preln_b, *pj_w1, *pj_b1, *pj_w2, *pj_b2;
   float *rope_cos = nullptr, *rope_sin = nullptr;
   // workspaces
-  DevBuf resid, xn, qkv, qb, attn, hbuf, meta, kv, logits, logits_tp, dec_f32, dec_bf16, part, img_feats, vis, pix, misc, tp_tmp;
+  DevBuf resid, xn, qkv, qb, attn, hbuf, meta, kv, logits, logits_tp, dec_f32, dec_bf16, part, img_feats, vis, pix, misc, tp_tmp, split_ws;
   // per-generation plan
   int B = 0, T = 0, S = 0, R = 0, Mtot = 0, max_new = 0, max_len = 0, max_splits = 1;
   int64_t kv_layer_stride = 0;
@@ -311,7 +311,7 @@ extern "C" void vdd_destroy(vdd_engine* e) {
   cudaDeviceSynchronize();
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   DevBuf* bufs[] = {&e->resid, &e->xn, &e->qkv, &e->qb, &e->attn, &e->hbuf, &e->meta, &e->kv, &e->logits, &e->logits_tp,
-                    &e->dec_f32, &e->dec_bf16, &e->part, &e->img_feats, &e->vis, &e->pix, &e->misc, &e->tp_tmp};
+                    &e->dec_f32, &e->dec_bf16, &e->part, &e->img_feats, &e->vis, &e->pix, &e->misc, &e->tp_tmp, &e->split_ws};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (e->arena) cudaFree(e->arena);
@@ -415,6 +415,11 @@ static int tp_allreduce_add(vdd_engine* e, float* partial, float* resid, int64_t
 static int do_gemm(vdd_engine* e, const void* a, const void* w, int M, int N, int K, int mode, const void* bias,
                    const int32_t* row_map, float* of32, void* obf16, int64_t ldc, cudaStream_t st) {
   GemmArgs g{a, w, M, N, K, mode, bias, row_map, of32, obf16, ldc};
+  if (mode == GEMM_OUT_ADD_F32 && M <= 128 && e->split_ws.p) {  // decode with > 8 fused rows: deterministic split-K
+    g.split_ws = (float*)e->split_ws.p;
+    g.split_ws_bytes = e->split_ws.bytes;
+    e->launches++;
+  }
   cudaError_t ce = launch_gemm(g, st);
   e->launches++;
   if (ce != cudaSuccess)
@@ -572,6 +577,7 @@ extern "C" int vdd_prefill(vdd_engine* e, const int64_t* ids, int B, int T, int 
   RC(ensure(e, e->hbuf, (size_t)Mtot * Il * 2));
   RC(ensure(e, e->kv, (size_t)2 * L * kv_total * 2));
   RC(ensure(e, e->logits, (size_t)R * c.vocab_size * 4));
+  if (R > 8 && R <= 128) RC(ensure(e, e->split_ws, (size_t)8 * R * H * 4));
   if (c.tp_size > 1) {
     RC(ensure(e, e->logits_tp, (size_t)R * c.vocab_size * 4));
     RC(ensure(e, e->tp_tmp, (size_t)(Mtot > R ? Mtot : R) * H * 4));

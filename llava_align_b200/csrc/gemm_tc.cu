@@ -125,16 +125,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int i = 0; i < 8; ++i) { v[2 * i] += bf16lo(bw[i]); v[2 * i + 1] += bf16hi(bw[i]); }
       }
       if (ep.mode == GEMM_OUT_F32 || ep.mode == GEMM_OUT_ADD_F32) {
-        float4* o = reinterpret_cast<float4*>(ep.out_f32 + orow * ep.ldc + col);
+        // split-K: slice z writes its partial to scratch plane z; reduce_splits_kernel adds the planes in order
+        float4* o = reinterpret_cast<float4*>(ep.out_f32 + (ep.splits > 1 ? (int64_t)blockIdx.z * ep.M * ep.ldc : 0) + orow * ep.ldc + col);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 t = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          if (ep.mode == GEMM_OUT_ADD_F32 && ep.splits > 1) {  // K-slices of one tile meet in the residual
-            float* of = reinterpret_cast<float*>(o + i);
-            atomicAdd(of, t.x); atomicAdd(of + 1, t.y); atomicAdd(of + 2, t.z); atomicAdd(of + 3, t.w);
-            continue;
-          }
-          if (ep.mode == GEMM_OUT_ADD_F32) {
+          if (ep.mode == GEMM_OUT_ADD_F32 && ep.splits == 1) {
             const float4 old = o[i];
             t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
           }
@@ -228,16 +224,21 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   ep.ldc = a.ldc;
   dim3 grid((a.N + GM_BN - 1) / GM_BN, (a.M + GM_BM - 1) / GM_BM);
   ep.splits = 1;
-  if (a.epilogue == GEMM_OUT_ADD_F32 && a.M <= GM_BM) {  // decode-sized residual GEMM: spread K over the idle SMs
+  if (a.epilogue == GEMM_OUT_ADD_F32 && a.M <= GM_BM && a.split_ws && !a.row_map && !a.bias) {
+    // decode-sized residual GEMM: N/128 tiles cannot fill 148 SMs, so spread K over the idle ones
     const int tiles = grid.x * grid.y, nkb = (a.K + GM_BK - 1) / GM_BK;
     int sp = 148 / (tiles > 0 ? tiles : 1);
     if (sp > nkb / 4) sp = nkb / 4;
     if (sp > 16) sp = 16;
+    while (sp > 1 && (size_t)sp * a.M * a.ldc * 4 > a.split_ws_bytes) --sp;
     if (sp > 1) ep.splits = sp;
   }
   grid.z = ep.splits;
+  if (ep.splits > 1) ep.out_f32 = a.split_ws;
   gemm_tc_kernel<<<grid, GM_THREADS, GM_SMEM, stream>>>(ta, tb, ep);
-  return cudaGetLastError();
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess || ep.splits == 1) return le;
+  return launch_reduce_splits(a.out_f32, a.split_ws, (int64_t)a.M * a.ldc, ep.splits, stream);
 }
 
 }  // namespace vdd

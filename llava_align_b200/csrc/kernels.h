@@ -64,6 +64,8 @@ struct GemmArgs {
   float* out_f32;
   void* out_bf16;
   int64_t ldc;
+  float* split_ws = nullptr;  // optional [splits, M, ldc] fp32 scratch: lets a decode-sized ADD GEMM split K deterministically
+  size_t split_ws_bytes = 0;
 };
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
 const char* gemm_init_error();
@@ -123,6 +125,7 @@ cudaError_t launch_decode_embed(const void* table_bf16, const int64_t* tokens, f
                                 cudaStream_t stream);
 cudaError_t launch_advance(int32_t* pos, int R, int32_t* step, cudaStream_t stream);  // pos[r] += 1, *step += 1
 cudaError_t launch_add_rows(float* dst, const float* src, int64_t n, cudaStream_t stream);
+cudaError_t launch_reduce_splits(float* dst, const float* ws, int64_t n, int splits, cudaStream_t stream);  // dst += sum_z ws[z]
 cudaError_t launch_cast_rows_bf16(const float* src, void* dst_bf16, int rows, int H, const int32_t* row_idx,
                                   cudaStream_t stream);
 
