@@ -45,13 +45,13 @@ constexpr int GV_STEP_BYTES = GV_RG * GV_UNIT * 2;  // 4 KB
 constexpr int GV_MAX_WARPS = 16;
 constexpr int GV_MAX_TASKS = 256;
 constexpr int GV_XPAD = 32;   // bf16 elements of padding per x row: rows land 64 B apart modulo 128 (no LDS conflicts)
-constexpr int GV_SMEM_BUDGET = 216 * 1024;
+constexpr int GV_SMEM_BUDGET = 222 * 1024;  // 227 KB per CTA minus the kernel's static shared memory
 
 struct GemvPlan {
   int n0, n1;  // CTA's feature band
   int ngroups, ks, ntasks, nunits;
 };
-__host__ __device__ __forceinline__ GemvPlan make_plan(int N, int K, int cta, int nctas, int nwarps) {
+__host__ __device__ __forceinline__ GemvPlan make_plan(int N, int K, int cta, int nctas, int ksmul) {
   GemvPlan p;
   const int pairs = N >> 1;
   p.n0 = 2 * (int)(((long long)cta * pairs) / nctas);
@@ -61,8 +61,7 @@ __host__ __device__ __forceinline__ GemvPlan make_plan(int N, int K, int cta, in
   p.nunits = (K + GV_UNIT - 1) / GV_UNIT;
   // the K-split must not depend on the warp count (which follows R through the shared-memory budget): a row's
   // result has to be bit-identical whatever other rows are fused beside it
-  (void)nwarps;
-  int ks = p.ngroups > 0 ? (8 * GV_MAX_WARPS + p.ngroups - 1) / p.ngroups : 1;
+  int ks = p.ngroups > 0 ? (ksmul * GV_MAX_WARPS + p.ngroups - 1) / p.ngroups : 1;
   const int ksmax = p.nunits / 2 > 1 ? p.nunits / 2 : 1;
   ks = ks < 1 ? 1 : (ks > ksmax ? ksmax : ks);
   p.ks = ks;
@@ -127,7 +126,7 @@ struct GemvCtx {
   int* task_next;   // shared counter: tasks are handed to warps on demand (balance does not depend on ntasks % nwarps)
   int* task_fifo;   // [nwarps][8]: ids grabbed by a warp's request iterator, replayed by its consume iterator
   uint32_t ring_warp;  // shared-space address of slot 0 of this warp's ring
-  int nwarps, g, t;
+  int nwarps, g, t, ksmul;
 };
 __device__ __forceinline__ void it_load(const GemvCtx& c, GemvIter& it, int task) {
   it.task = task;
@@ -185,7 +184,7 @@ __device__ __forceinline__ void ring_request(const GemvCtx& c, const __nv_bfloat
 // Part 1 of a projection: plan, task table, first GV_D-1 ring steps.  Touches only weights (never activations).
 __device__ __forceinline__ void phase_begin(const GemvArgs& a, GemvCtx& c) {
   const int tid = threadIdx.x, nthreads = blockDim.x, warp = tid >> 5;
-  c.p = make_plan(a.N, a.K, blockIdx.x, gridDim.x, c.nwarps);
+  c.p = make_plan(a.N, a.K, blockIdx.x, gridDim.x, c.ksmul);
   for (int i = tid; i < c.p.ntasks; i += nthreads) {
     const int gi = i / c.p.ks, ji = i - gi * c.p.ks;
     c.task_tab[i] = make_int4(gi, (ji * c.p.nunits) / c.p.ks, ((ji + 1) * c.p.nunits) / c.p.ks, ji);
@@ -231,68 +230,70 @@ __device__ __forceinline__ void phase_rest(const GemvArgs& a, GemvCtx& c, unsign
   }
   // ---- prologue: stage x (bf16) in shared memory.  Loads go to L2 (.cg): the producer may be another CTA of this launch.
   if (a.x_resid) {
-    // RMSNorm.  The sum of squares is formed per 128-element chunk (one warp load, fixed shuffle tree) and the chunk
-    // sums are added in chunk order, so rstd -- and with it every output bit -- does not depend on how many warps the
-    // launch has (which follows R through the shared-memory budget).
+    // RMSNorm.  (The launcher picks the thread count from K and the row CLASS (<=4 / <=8 rows), never from R itself,
+    // so the reduction order below -- and with it every output bit of a row -- is the same whatever is fused beside it.)
     const __nv_bfloat16* nw = reinterpret_cast<const __nv_bfloat16*>(a.norm_w);
-    const int lane = tid & 31, nwarps = nthreads >> 5;
-    const int nchunks = K / 128;  // host guarantees K % 128 == 0 for this prologue
-    float* csum = part;           // [R][nchunks] scratch (part is not in use yet)
-    constexpr int MAXC = R <= 4 ? 3 : 1;
-    float4 keep[R][MAXC];
-    const bool kept = nchunks <= MAXC * nwarps;
-#pragma unroll
-    for (int q = 0; q < MAXC; ++q) {
-      const int ch = q * nwarps + warp;
-      if (ch < nchunks) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) keep[r][q] = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + ch * 128) + lane);
-      }
-    }
-    for (int ch = warp, q = 0; ch < nchunks; ch += nwarps, ++q) {
+    constexpr int PASS = R <= 3 ? 4 : (R <= 4 ? 3 : 1);  // float4 per thread per row held in registers
+    if (K <= PASS * 4 * nthreads) {
+      float4 xv[R][PASS];
+      float ss[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        float4 xv;
-        if (q < MAXC) {
-          xv = keep[r][0];
+        ss[r] = 0.f;
 #pragma unroll
-          for (int qq = 1; qq < MAXC; ++qq) if (q == qq) xv = keep[r][qq];
-        } else {
-          xv = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + ch * 128) + lane);
+        for (int q = 0; q < PASS; ++q) {
+          const int k = (q * nthreads + tid) * 4;
+          xv[r][q] = k < K ? __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float v = xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) csum[r * nchunks + ch] = v;
       }
-    }
-    __syncthreads();
-    float rstd[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float tot = 0.f;
-      for (int ch = 0; ch < nchunks; ++ch) tot += csum[r * nchunks + ch];
-      rstd[r] = rsqrtf(tot / (float)K + a.eps);
-    }
-    __syncthreads();  // csum aliases part
-    for (int ch = warp, q = 0; ch < nchunks; ch += nwarps, ++q) {
-      const int k = ch * 128 + lane * 4;
-      const uint2 wv = *reinterpret_cast<const uint2*>(nw + k);
-      const float w0 = bf16lo(wv.x), w1 = bf16hi(wv.x), w2 = bf16lo(wv.y), w3 = bf16hi(wv.y);
+      for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        float4 xv;
-        if (kept && q < MAXC) {
-          xv = keep[r][0];
+        for (int q = 0; q < PASS; ++q)
+          ss[r] += xv[r][q].x * xv[r][q].x + xv[r][q].y * xv[r][q].y + xv[r][q].z * xv[r][q].z + xv[r][q].w * xv[r][q].w;
+      float rstd[R];
 #pragma unroll
-          for (int qq = 1; qq < MAXC; ++qq) if (q == qq) xv = keep[r][qq];
-        } else {
-          xv = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k));
+      for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(block_reduce<false>(ss[r], red) / (float)K + a.eps);
+#pragma unroll
+      for (int q = 0; q < PASS; ++q) {
+        const int k = (q * nthreads + tid) * 4;
+        if (k < K) {
+          const uint2 wv = *reinterpret_cast<const uint2*>(nw + k);
+          const float w0 = bf16lo(wv.x), w1 = bf16hi(wv.x), w2 = bf16lo(wv.y), w3 = bf16hi(wv.y);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            uint2 o;
+            o.x = pack_bf16(xv[r][q].x * rstd[r] * w0, xv[r][q].y * rstd[r] * w1);
+            o.y = pack_bf16(xv[r][q].z * rstd[r] * w2, xv[r][q].w * rstd[r] * w3);
+            *reinterpret_cast<uint2*>(xs + (size_t)r * XS + k) = o;
+          }
         }
-        uint2 o;
-        o.x = pack_bf16(xv.x * rstd[r] * w0, xv.y * rstd[r] * w1);
-        o.y = pack_bf16(xv.z * rstd[r] * w2, xv.w * rstd[r] * w3);
-        *reinterpret_cast<uint2*>(xs + (size_t)r * XS + k) = o;
+      }
+    } else {  // wide rows: two passes over L2
+      float ss[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) ss[r] = 0.f;
+      for (int k = tid * 4; k < K; k += nthreads * 4) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 xv = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k));
+          ss[r] += xv.x * xv.x + xv.y * xv.y + xv.z * xv.z + xv.w * xv.w;
+        }
+      }
+      float rstd[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(block_reduce<false>(ss[r], red) / (float)K + a.eps);
+      for (int k = tid * 4; k < K; k += nthreads * 4) {
+        const uint2 wv = *reinterpret_cast<const uint2*>(nw + k);
+        const float w0 = bf16lo(wv.x), w1 = bf16hi(wv.x), w2 = bf16lo(wv.y), w3 = bf16hi(wv.y);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 xv = __ldcg(reinterpret_cast<const float4*>(a.x_resid + (size_t)r * K + k));
+          uint2 o;
+          o.x = pack_bf16(xv.x * rstd[r] * w0, xv.y * rstd[r] * w1);
+          o.y = pack_bf16(xv.z * rstd[r] * w2, xv.w * rstd[r] * w3);
+          *reinterpret_cast<uint2*>(xs + (size_t)r * XS + k) = o;
+        }
       }
     }
   } else {
@@ -393,6 +394,7 @@ __global__ void __launch_bounds__(GV_MAX_WARPS * 32, 1) gemv_kernel(const GemvCh
   c.task_next = &task_next;
   c.task_fifo = task_fifo;
   c.nwarps = blockDim.x >> 5;
+  c.ksmul = ch.ksmul;
   c.g = (threadIdx.x & 31) >> 2;
   c.t = threadIdx.x & 3;
   c.ring_warp = smem_u32(smem) + (uint32_t)(threadIdx.x >> 5) * GV_D * GV_STEP_BYTES;
@@ -424,12 +426,17 @@ __global__ void __launch_bounds__(GV_MAX_WARPS * 32, 1) gemv_kernel(const GemvCh
   }
 }
 
-static size_t gemv_smem(const GemvArgs& a, int grid, int nwarps) {
-  const int pairs = a.N / 2;
-  const int nrows_max = 2 * ((pairs + grid - 1) / grid) + 2;
-  const size_t xbytes = (size_t)a.R * (a.K + GV_XPAD) * 2;
-  const size_t part = (size_t)(64 * GV_MAX_WARPS + 2 * nrows_max + 64) * a.R * 4;  // >= rows*ks of any CTA
-  return (size_t)nwarps * GV_D * GV_STEP_BYTES + xbytes + part;
+static size_t gemv_smem(const GemvArgs& a, int grid, int nwarps, int ksmul) {
+  const int Rc = a.R <= 4 ? 4 : 8;  // row class: the warp count must not depend on R itself (see the RMSNorm prologue)
+  size_t entries = 0;  // max over CTAs of (8-row groups) * 8 * ks  >=  rows * ks
+  for (int cta = 0; cta < grid; ++cta) {
+    const GemvPlan p = make_plan(a.N, a.K, cta, grid, ksmul);
+    const size_t e = (size_t)p.ngroups * GV_RG * p.ks;
+    entries = e > entries ? e : entries;
+  }
+  const size_t xbytes = (size_t)Rc * (a.K + GV_XPAD) * 2;
+  const size_t part = entries * Rc * 4;
+  return (size_t)nwarps * GV_D * GV_STEP_BYTES + xbytes + part + 64;
 }
 
 cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaStream_t stream) {
@@ -439,10 +446,15 @@ cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaSt
   for (int i = 0; i < ch.n; ++i) {
     const GemvArgs& a = ch.ph[i];
     if (a.R != R || a.R < 1 || a.R > 8 || (a.K % 8) != 0 || (a.N % 2) != 0) return cudaErrorInvalidValue;
-    if (a.x_resid && (a.epilogue == GEMV_OUT_ADD_RESID || (a.K % 128) != 0)) return cudaErrorInvalidValue;
+    if (a.x_resid && a.epilogue == GEMV_OUT_ADD_RESID) return cudaErrorInvalidValue;
     if (a.N / 2 < grid) grid = a.N / 2;
   }
   if (ch.n > 1 && (!ch.barrier || grid > num_sms)) return cudaErrorInvalidValue;
+  int ksmul = 8;
+  if (const char* ev = getenv("VDD_GV_KSMUL")) {  // tuning knob: ~ksmul*16 warp tasks per CTA
+    const int v = atoi(ev);
+    if (v >= 1 && v <= 8) ksmul = v;
+  }
   // one CTA per SM; as many warps (each with its private 3-step ring) as shared memory allows next to x
   int nwarps = GV_MAX_WARPS;
   if (const char* ev = getenv("VDD_GV_WARPS")) {  // tuning knob
@@ -453,7 +465,7 @@ cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaSt
   for (; nwarps >= 1; nwarps -= (nwarps > 4 ? 2 : 1)) {
     smem = 0;
     for (int i = 0; i < ch.n; ++i) {
-      const size_t s = gemv_smem(ch.ph[i], grid, nwarps);
+      const size_t s = gemv_smem(ch.ph[i], grid, nwarps, ksmul);
       smem = s > smem ? s : smem;
     }
     if (smem <= (size_t)GV_SMEM_BUDGET) break;
@@ -482,7 +494,9 @@ cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaSt
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, ch);
+  GemvChain chl = ch;
+  chl.ksmul = ksmul;
+  return cudaLaunchKernelEx(&cfg, kern, chl);
 }
 
 cudaError_t launch_gemv(const GemvArgs& a, int num_sms, bool pdl, cudaStream_t stream) {

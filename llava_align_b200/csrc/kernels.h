@@ -40,6 +40,7 @@ cudaError_t launch_gemv(const GemvArgs& a, int num_sms, bool pdl, cudaStream_t s
 struct GemvChain {
   GemvArgs ph[4];
   int n;
+  int ksmul = 8;  // set by the launcher
   unsigned* barrier;
   unsigned long long* trace;  // debug: [grid][4 phases][8 slots] globaltimer stamps of thread 0, or null
 };

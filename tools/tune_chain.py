@@ -13,11 +13,8 @@ ids, img = synthetic_inputs(m.vdd_config, 1, 32)
 params = E.make_sample_params(cd_alpha=1.0, cd_beta=0.1, use_contrast=True, eos_token_id=None)
 eng.generate(ids, img.cuda(), True, True, params, 8, None, None)
 lib = _lib.load()
-for w in [None, 16, 14, 12, 10, 8, 6]:
-    if w is None:
-        os.environ.pop("VDD_GV_WARPS", None)
-    else:
-        os.environ["VDD_GV_WARPS"] = str(w)
+for w in [8, 6, 4, 3, 2, 1]:
+    os.environ["VDD_GV_KSMUL"] = str(w)
     with torch.cuda.stream(eng.stream):
         for _ in range(3):
             _lib.check(lib.vdd_bench_projection_chain(eng.h, eng.stream.cuda_stream), "chain")
@@ -28,4 +25,4 @@ for w in [None, 16, 14, 12, 10, 8, 6]:
         e1.record(eng.stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
-    print(f"warps={w}: chain {ms:.3f} ms -> {13.2147 / ms:.1f} GB/ms = {13214.7 / ms / 6548.2:.3f} of peak", flush=True)
+    print(f"ksmul={w}: chain {ms:.3f} ms -> {13.2147 / ms:.1f} GB/ms = {13214.7 / ms / 6548.2:.3f} of peak", flush=True)
