@@ -127,6 +127,7 @@ struct GemvCtx {
   int* task_fifo;   // [nwarps][8]: ids grabbed by a warp's request iterator, replayed by its consume iterator
   uint32_t ring_warp;  // shared-space address of slot 0 of this warp's ring
   int nwarps, g, t, ksmul;
+  uint2 nwv[4];  // RMSNorm weights of this thread's columns, fetched before the grid barrier (they are static)
 };
 __device__ __forceinline__ void it_load(const GemvCtx& c, GemvIter& it, int task) {
   it.task = task;
@@ -190,6 +191,14 @@ __device__ __forceinline__ void phase_begin(const GemvArgs& a, GemvCtx& c) {
     c.task_tab[i] = make_int4(gi, (ji * c.p.nunits) / c.p.ks, ((ji + 1) * c.p.nunits) / c.p.ks, ji);
   }
   if (tid == 0) *c.task_next = 0;
+  if (a.x_resid) {
+    const __nv_bfloat16* nw = reinterpret_cast<const __nv_bfloat16*>(a.norm_w);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = (q * nthreads + tid) * 4;
+      c.nwv[q] = k < a.K ? __ldg(reinterpret_cast<const uint2*>(nw + k)) : make_uint2(0u, 0u);
+    }
+  }
   __syncthreads();
   (void)warp;
   c.pi.seq = 0;
@@ -258,7 +267,7 @@ __device__ __forceinline__ void phase_rest(const GemvArgs& a, GemvCtx& c, unsign
       for (int q = 0; q < PASS; ++q) {
         const int k = (q * nthreads + tid) * 4;
         if (k < K) {
-          const uint2 wv = *reinterpret_cast<const uint2*>(nw + k);
+          const uint2 wv = c.nwv[q];
           const float w0 = bf16lo(wv.x), w1 = bf16hi(wv.x), w2 = bf16lo(wv.y), w3 = bf16hi(wv.y);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
