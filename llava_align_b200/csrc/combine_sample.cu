@@ -10,6 +10,9 @@
 // HBM-bound: algorithmic bytes per sequence = S*V*4 read (+V*4 q, +V*4 scores when requested).
 // Every fp32 operation that decides set membership is written with explicit round-to-nearest intrinsics in
 // the reference's operation order (no FMA contraction), so scores are bit-identical to torch fp32 on the same inputs.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -310,7 +313,156 @@ __global__ void __launch_bounds__(CS_THREADS, 1) combine_sample_kernel(const Sam
   }
 }
 
+// ------------------------------------------------------------------------------------------------ cluster fast path
+// When no ordering is needed (no top-p, and top-k absent or == 1) a row is split over a thread-block CLUSTER of 8 CTAs
+// (256 threads, 16 values per thread): eight times the loads in flight per row and several rows resident per SM, with
+// the four row-wide reductions (max l, max s, sum exp, arg-max of the race) done through distributed shared memory.
+// Same arithmetic, same operation order per element as the single-CTA kernel => bit-identical scores and tokens.
+namespace cg = cooperative_groups;
+constexpr int CC_CL = 8, CC_THREADS = 256, CC_ITEMS = 16;  // V <= 8 * 256 * 16 = 32768
+
+__device__ __forceinline__ float cluster_reduce_f(cg::cluster_group& cl, float v, float* slots, float* red, bool is_max) {
+  v = is_max ? block_reduce<true>(v, red) : block_reduce<false>(v, red);
+  if (threadIdx.x == 0) slots[0] = v;  // slots: this CTA's published value for this reduction
+  cl.sync();
+  float r = is_max ? -INFINITY : 0.f;
+#pragma unroll
+  for (int k = 0; k < CC_CL; ++k) {  // fixed order => every CTA computes the same bits
+    const float o = *cl.map_shared_rank(slots, k);
+    r = is_max ? fmaxf(r, o) : r + o;
+  }
+  return r;
+}
+
+__global__ void __cluster_dims__(CC_CL, 1, 1) __launch_bounds__(CC_THREADS)
+combine_sample_cluster_kernel(const SampleArgs byval, const SampleArgs* dptr) {
+  __shared__ float redf[33];
+  __shared__ float pub[4];                 // one published value per reduction (no slot is reused => no extra syncs)
+  __shared__ unsigned long long pub_best;
+  __shared__ unsigned long long best_s;
+  cg::cluster_group cl = cg::this_cluster();
+  const SampleArgs& a = dptr ? *dptr : byval;
+  const int rank = (int)cl.block_rank();
+  const int b = blockIdx.x / CC_CL, tid = threadIdx.x;
+  const int V = a.V;
+  const int step = a.step_ptr ? *a.step_ptr : 0;
+  const float* l = a.l + (int64_t)b * a.ld;
+  const float* u = a.u ? a.u + (int64_t)b * a.ld : nullptr;
+  const float* d = a.d ? a.d + (int64_t)b * a.ld : nullptr;
+  const int64_t so = ((int64_t)step * a.B + b) * V;
+  const float* q = a.q ? a.q + so : nullptr;
+  float* scores_out = a.scores_out ? a.scores_out + so : nullptr;
+  const bool contrast = a.use_contrast && (u || d);
+  const int e0 = rank * (CC_THREADS * CC_ITEMS) + tid;  // element j of this thread: e0 + j*256
+
+  float v[CC_ITEMS], cu[CC_ITEMS], cd[CC_ITEMS];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < CC_ITEMS; ++j) {  // every load of the row slice is issued before anything is consumed
+    const int e = e0 + j * CC_THREADS;
+    v[j] = e < V ? __ldg(l + e) : -INFINITY;
+    cu[j] = (contrast && u && e < V) ? __ldg(u + e) : 0.f;
+    cd[j] = (contrast && d && e < V) ? __ldg(d + e) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < CC_ITEMS; ++j) mx = fmaxf(mx, v[j]);
+  mx = cluster_reduce_f(cl, mx, &pub[0], redf, true);
+  if (contrast) {
+    const float cutoff = __fadd_rn(a.log_beta, mx);
+    const float a1 = a.one_plus_alpha, al = a.alpha;
+#pragma unroll
+    for (int j = 0; j < CC_ITEMS; ++j) {
+      const int e = e0 + j * CC_THREADS;
+      if (e < V) {
+        const float c = (u && d) ? __fmul_rn(__fadd_rn(cu[j], cd[j]), 0.5f) : (u ? cu[j] : cd[j]);
+        const float s = __fsub_rn(__fmul_rn(a1, v[j]), __fmul_rn(al, c));
+        v[j] = v[j] < cutoff ? -INFINITY : s;
+      }
+    }
+  }
+  if (a.temperature != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < CC_ITEMS; ++j) v[j] = __fdiv_rn(v[j], a.temperature);
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < CC_ITEMS; ++j) m = fmaxf(m, v[j]);
+  m = cluster_reduce_f(cl, m, &pub[1], redf, true);
+  if (a.top_k == 1) {  // TopK(1): everything below the maximum goes (ties stay)
+#pragma unroll
+    for (int j = 0; j < CC_ITEMS; ++j)
+      if (v[j] < m) v[j] = -INFINITY;
+  }
+#pragma unroll
+  for (int j = 0; j < CC_ITEMS; ++j) {
+    const int e = e0 + j * CC_THREADS;
+    if (scores_out && e < V) scores_out[e] = v[j];
+  }
+  if (q) {
+    float qv[CC_ITEMS];
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < CC_ITEMS; ++j) {
+      const int e = e0 + j * CC_THREADS;
+      qv[j] = e < V ? __ldg(q + e) : 1.f;
+      v[j] = expf(v[j] - m);
+      z += v[j];
+    }
+    z = cluster_reduce_f(cl, z, &pub[2], redf, false);
+    const float rz = 1.0f / z;
+#pragma unroll
+    for (int j = 0; j < CC_ITEMS; ++j) {
+      const int e = e0 + j * CC_THREADS;
+      v[j] = e < V ? __fdividef(v[j] * rz, qv[j]) : -1.f;
+    }
+  }
+  unsigned long long best = 0ull;
+#pragma unroll
+  for (int j = 0; j < CC_ITEMS; ++j) {
+    const int e = e0 + j * CC_THREADS;
+    if (e < V) {
+      unsigned kb = __float_as_uint(v[j]);
+      kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
+      const unsigned long long p = ((unsigned long long)kb << 32) | (unsigned)(0x7fffffff - e);
+      best = p > best ? p : best;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+    best = t > best ? t : best;
+  }
+  if (tid == 0) best_s = 0ull;
+  __syncthreads();
+  if ((tid & 31) == 0) atomicMax(&best_s, best);
+  __syncthreads();
+  if (tid == 0) pub_best = best_s;
+  cl.sync();
+  if (rank == 0 && tid == 0) {
+    unsigned long long bb = 0ull;
+    for (int k = 0; k < CC_CL; ++k) {
+      const unsigned long long o = *cl.map_shared_rank(&pub_best, k);
+      bb = o > bb ? o : bb;
+    }
+    long long tok = 0x7fffffff - (int)(bb & 0xffffffffull);
+    if (a.eos >= 0 && a.unfinished) {
+      const int unf = a.unfinished[b];
+      tok = tok * unf + a.pad * (1 - unf);
+      a.unfinished[b] = (unf != 0 && tok != a.eos) ? 1 : 0;
+    }
+    if (a.tokens_out) a.tokens_out[b] = tok;
+    if (a.seq_out) a.seq_out[(int64_t)b * a.seq_ld + step] = tok;
+  }
+  cl.sync();  // nobody leaves while a peer may still read its shared memory
+}
+
 cudaError_t launch_combine_sample(const SampleArgs& args, const SampleArgs* dptr, int B, int V, cudaStream_t stream) {
+  // host copy of the warper settings decides the kernel (the device struct, when used, holds the same values)
+  const bool needs_order = args.top_p < 1.0f || (args.top_k > 1 && args.top_k < V);
+  if (!needs_order && V <= CC_CL * CC_THREADS * CC_ITEMS && getenv("VDD_K8_SINGLE_CTA") == nullptr) {
+    combine_sample_cluster_kernel<<<B * CC_CL, CC_THREADS, 0, stream>>>(args, dptr);
+    return cudaGetLastError();
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(combine_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);

@@ -879,6 +879,8 @@ extern "C" int vdd_generate(vdd_engine* e, const int64_t* ids, int B, int T, con
   int steps = 1;
   if (max_new > 1) {
     const uint64_t key = ((uint64_t)B << 40) ^ ((uint64_t)S << 32) ^ ((uint64_t)e->max_splits << 16) ^ (uint64_t)(e->use_pdl ? 1 : 0) ^ (uint64_t)(e->use_fused ? 2 : 0) ^
+                         (uint64_t)((a.top_p < 1.0f || (a.top_k > 1 && a.top_k < V)) ? 4 : 0) ^  // which K8 kernel the graph holds
+                        
                          ((uint64_t)(uintptr_t)e->kv.p << 1) ^ (uint64_t)(uintptr_t)e->logits.p ^ ((uint64_t)e->kv_layer_stride << 3);
     int per_step_launches = 0;
     const bool graph = e->use_graph && st != nullptr;  // the legacy default stream cannot be captured
