@@ -334,7 +334,7 @@ __device__ __forceinline__ float cluster_reduce_f(cg::cluster_group& cl, float v
   return r;
 }
 
-__global__ void __cluster_dims__(CC_CL, 1, 1) __launch_bounds__(CC_THREADS)
+__global__ void __cluster_dims__(CC_CL, 1, 1) __launch_bounds__(CC_THREADS, 4)
 combine_sample_cluster_kernel(const SampleArgs byval, const SampleArgs* dptr) {
   __shared__ float redf[33];
   __shared__ float pub[4];                 // one published value per reduction (no slot is reused => no extra syncs)

@@ -118,7 +118,6 @@ cudaError_t launch_rope_kv_prefill(const float* qkv, int rows, int heads, int D,
                                    const int32_t* row_pos, const int64_t* kv_off, const int32_t* kv_cap,
                                    const float* rope_cos, const float* rope_sin, void* q_out_bf16, void* kcache,
                                    void* vcache, cudaStream_t stream);
-cudaError_t launch_rope_table(float* cos_t, float* sin_t, int max_pos, int D, float theta, cudaStream_t stream);
 cudaError_t launch_im2col(const void* pixels_bf16, void* out_bf16, int B, int S, int P, int Kpad, cudaStream_t stream);
 cudaError_t launch_vit_embed(const float* patch_out, const void* cls_bf16, const void* pos_bf16, float* resid, int B,
                              int NP, int H, cudaStream_t stream);
