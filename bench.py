@@ -137,7 +137,7 @@ def run_reference(a):
                              "phases": {k: last[k] for k in ("vision_s", "prefill_s", "decode_s_per_token")}},
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(a, cfg, n, mode="dp"):
@@ -151,8 +151,25 @@ def workload_config(a, cfg, n, mode="dp"):
             "l2_policy": "inputs larger than L2: every step streams the 13.2 GB of weights (L2 = 126 MB); no flush needed"}
 
 
+def _emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (e.g. NCCL's version banner) was
+    diverted to stderr by _divert_stdout()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _divert_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     a = parse()
+    _divert_stdout()
     if a.profile:
         a.no_e2e = a.no_cpu_baseline = True
     if a.impl == "reference":
@@ -218,11 +235,16 @@ def main():
             ms = float(t.item())
         return ms, eng.launch_count()
 
+    def note(msg):
+        print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    note(f"model loaded (world {world}, parallel {a.parallel}, tp {tp})")
     sampler = ClockSampler(local) if rank == 0 else None
     # ---- value: inputs resident in HBM
     dev_fn = lambda: eng.generate(ids, img_dev, True, True, params, n_new, q, None)
     ms, launches = timed(dev_fn, a.warmup, a.steps)
     tm = eng.last_timings()
+    note(f"device-resident leg done: {ms:.1f} ms for {a.steps} steps")
     replicas = world if tp == 1 else 1  # dp: every rank generated its own B x n_new tokens in the (max-over-ranks) time
     value = replicas * B * n_new * a.steps / (ms / 1e3)
     # ---- e2e: the reference-facing call with pinned host buffers (H2D pixels, D2H tokens inside)
@@ -239,6 +261,7 @@ def main():
                "d2h_bytes_per_step": int(replicas * B * n_new * 8),
                "ms_per_step": ms2 / a.steps}
     clocks = sampler.stop() if sampler else None
+    note("e2e leg done")
 
     # ---- roofline of the dominant kernel (gemv_kernel: every projection of the decode step), timed live with CUDA events
     proj_bytes, kv_tok = algorithmic_bytes(cfg, tp)
@@ -319,13 +342,14 @@ def main():
         r = cb.ReferenceSample(cfg, B=B, T=T, n_new=3).run()
         cpu = {"value": cb.tokens_per_s(r, B, n_new), "unit": "tokens/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
                "phases": {k: r[k] for k in ("vision_s", "prefill_s", "decode_s_per_token")}}
+    note("all legs done")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(a, cfg, world, a.parallel),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * replicas, "roofline": roofline, "decode_step": decode,
                 "logit_combine": combine, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
