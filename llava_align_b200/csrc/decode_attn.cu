@@ -11,6 +11,9 @@
 // the last CTA to arrive for a (row, head) merges them (threadfence + counter), so the launch is self-contained.
 // HBM bytes: ctx*2*D*2 per (row, head) -- the kernel is a pure KV stream; K/V are read as 16-byte pieces, 16
 // lanes per token (256 B contiguous); all 16 loads of a lane are issued before any is consumed.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -160,7 +163,168 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
   out[tid] = __float2bfloat16_rn(acc / LL);
 }
 
+// ------------------------------------------------------------------------------------------------ cluster variant
+// One thread-block CLUSTER of 8 CTAs per (row, head): every CTA takes one eighth of the context, and the eight partial
+// (m, l, o[128]) are merged through distributed shared memory after one cluster barrier -- no global partials, no
+// fence + atomic + "last CTA" round trips, no idle CTAs for the short debias rows.  Same per-token arithmetic as above.
+namespace cg = cooperative_groups;
+constexpr int DC_CL = 8;
+constexpr int DC_TPG = 8;   // tokens per 16-lane group per pass => 64 tokens per CTA per pass (registers: 6 CTAs per SM, one wave)
+
+__global__ void __cluster_dims__(1, DC_CL, 1) __launch_bounds__(DA_THREADS, 6) decode_attn_cluster_kernel(const DecodeAttnArgs a) {
+  __shared__ float q_s[DA_D];
+  __shared__ __align__(16) __nv_bfloat16 knew_s[DA_D];
+  __shared__ __align__(16) __nv_bfloat16 vnew_s[DA_D];
+  __shared__ float o_s[8][DA_D];
+  __shared__ float ml_s[8][2];
+  __shared__ float pub_o[DA_D];  // this CTA's partial, read by its cluster peers
+  __shared__ float pub_ml[2];
+  cg::cluster_group cl = cg::this_cluster();
+  const int rh = blockIdx.x, rank = blockIdx.y;
+  const int r = rh / a.heads, h = rh - r * a.heads;
+  const int tid = threadIdx.x;
+  const int Hl = a.heads * DA_D;
+  const int grp = tid >> 4, gl = tid & 15;
+  const int cap = a.kv_cap[r];
+  __nv_bfloat16* Kc = reinterpret_cast<__nv_bfloat16*>(a.kcache) + a.kv_off[r] + (size_t)h * cap * DA_D;
+  __nv_bfloat16* Vc = reinterpret_cast<__nv_bfloat16*>(a.vcache) + a.kv_off[r] + (size_t)h * cap * DA_D;
+  // pos and the cached tokens < pos are older than the immediate predecessor kernel: safe before the dependency wait
+  const int pos = a.pos[r];
+  const int ctx = pos + 1;
+  const int span = ((ctx + DC_CL - 1) / DC_CL + 7) & ~7;  // tokens per CTA, a multiple of the 8 groups
+  const int t_begin = rank * span, t_end = min(ctx, t_begin + span);
+  const bool owns_new = pos >= t_begin && pos < t_end;
+
+  float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  bool waited = false;
+  float qr[8];
+  for (int p0 = t_begin; p0 < t_end || !waited; p0 += 8 * DC_TPG) {
+    uint4 kr[DC_TPG], vr[DC_TPG];
+#pragma unroll
+    for (int j = 0; j < DC_TPG; ++j) {
+      const int t = p0 + grp + 8 * j;
+      kr[j] = make_uint4(0u, 0u, 0u, 0u);
+      vr[j] = kr[j];
+      if (t < t_end && t < pos) {
+        kr[j] = *reinterpret_cast<const uint4*>(Kc + (size_t)t * DA_D + gl * 8);
+        vr[j] = *reinterpret_cast<const uint4*>(Vc + (size_t)t * DA_D + gl * 8);
+      }
+    }
+    if (!waited) {
+      waited = true;
+      pdl_wait();
+      pdl_launch_dependents();
+      const float* qkv = a.qkv + (size_t)r * 3 * Hl;
+      const int i = tid & 63;
+      const float c = a.rope_cos[(size_t)pos * (DA_D / 2) + i], s = a.rope_sin[(size_t)pos * (DA_D / 2) + i];
+      const float* qh = qkv + h * DA_D;
+      const float x1 = qh[i], x2 = qh[i + 64];
+      q_s[tid] = tid < 64 ? (x1 * c - x2 * s) : (x2 * c + x1 * s);
+      if (owns_new) {
+        const float* kh = qkv + Hl + h * DA_D;
+        const float k1 = kh[i], k2 = kh[i + 64];
+        const __nv_bfloat16 kb = __float2bfloat16_rn(tid < 64 ? (k1 * c - k2 * s) : (k2 * c + k1 * s));
+        const __nv_bfloat16 vb = __float2bfloat16_rn(qkv[2 * Hl + h * DA_D + tid]);
+        Kc[(size_t)pos * DA_D + tid] = kb;
+        Vc[(size_t)pos * DA_D + tid] = vb;
+        knew_s[tid] = kb;
+        vnew_s[tid] = vb;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i2 = 0; i2 < 8; ++i2) qr[i2] = q_s[gl * 8 + i2];
+    }
+    float sc[DC_TPG];
+    float mp = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < DC_TPG; ++j) {
+      const int t = p0 + grp + 8 * j;
+      if (t == pos && owns_new) {
+        kr[j] = *reinterpret_cast<const uint4*>(knew_s + gl * 8);
+        vr[j] = *reinterpret_cast<const uint4*>(vnew_s + gl * 8);
+      }
+      float s = bf16lo(kr[j].x) * qr[0] + bf16hi(kr[j].x) * qr[1] + bf16lo(kr[j].y) * qr[2] + bf16hi(kr[j].y) * qr[3] +
+                bf16lo(kr[j].z) * qr[4] + bf16hi(kr[j].z) * qr[5] + bf16lo(kr[j].w) * qr[6] + bf16hi(kr[j].w) * qr[7];
+#pragma unroll
+      for (int x = 8; x > 0; x >>= 1) s += __shfl_xor_sync(0xffffffffu, s, x);
+      sc[j] = t < t_end ? s * a.scale : -INFINITY;
+      mp = fmaxf(mp, sc[j]);
+    }
+    const float mn = fmaxf(m, mp);
+    const float corr = mn == -INFINITY ? 1.f : expf(m - mn);  // exp(-inf) = 0 on the first pass
+    l *= corr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] *= corr;
+    m = mn;
+#pragma unroll
+    for (int j = 0; j < DC_TPG; ++j) {
+      const float p = m == -INFINITY ? 0.f : expf(sc[j] - m);
+      l += p;
+      o[0] = fmaf(p, bf16lo(vr[j].x), o[0]); o[1] = fmaf(p, bf16hi(vr[j].x), o[1]);
+      o[2] = fmaf(p, bf16lo(vr[j].y), o[2]); o[3] = fmaf(p, bf16hi(vr[j].y), o[3]);
+      o[4] = fmaf(p, bf16lo(vr[j].z), o[4]); o[5] = fmaf(p, bf16hi(vr[j].z), o[5]);
+      o[6] = fmaf(p, bf16lo(vr[j].w), o[6]); o[7] = fmaf(p, bf16hi(vr[j].w), o[7]);
+    }
+  }
+  // ---- merge the 8 groups of this CTA (fixed order), publish, merge the 8 CTAs of the cluster
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o_s[grp][gl * 8 + i] = o[i];
+  if (gl == 0) { ml_s[grp][0] = m; ml_s[grp][1] = l; }
+  __syncthreads();
+  {
+    float M = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) M = fmaxf(M, ml_s[g][0]);
+    float L = 0.f, od = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float w = ml_s[g][0] == -INFINITY ? 0.f : expf(ml_s[g][0] - M);
+      L += ml_s[g][1] * w;
+      od += o_s[g][tid] * w;
+    }
+    pub_o[tid] = od;
+    if (tid == 0) { pub_ml[0] = M; pub_ml[1] = L; }
+  }
+  cl.sync();
+  if (tid < DA_D / DC_CL) {  // this CTA finishes 16 of the 128 output dims
+    const int dim = rank * (DA_D / DC_CL) + tid;
+    float mk[DC_CL], MM = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < DC_CL; ++k) {
+      mk[k] = cl.map_shared_rank(pub_ml, k)[0];
+      MM = fmaxf(MM, mk[k]);
+    }
+    float LL = 0.f, acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < DC_CL; ++k) {
+      const float w = mk[k] == -INFINITY ? 0.f : expf(mk[k] - MM);
+      LL += cl.map_shared_rank(pub_ml, k)[1] * w;
+      acc += cl.map_shared_rank(pub_o, k)[dim] * w;
+    }
+    reinterpret_cast<__nv_bfloat16*>(a.out_bf16)[(size_t)r * Hl + h * DA_D + dim] = __float2bfloat16_rn(acc / LL);
+  }
+  cl.sync();  // nobody leaves while a peer may still read its shared memory
+}
+
 cudaError_t launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t stream) {
+  // Measured on B200 (bench.py, config 2): global-partials kernel 2.853 ms per decode step, cluster kernel 3.085 ms --
+  // cluster scheduling + two cluster barriers cost more than fence + atomic + last-CTA merge at these sizes.  The
+  // cluster variant stays available for experiments.
+  static const bool cluster_kernel = getenv("VDD_ATTN_CLUSTER") != nullptr;
+  if (cluster_kernel) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(a.R * a.heads, DC_CL);
+    cfg.blockDim = dim3(DA_THREADS);
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, decode_attn_cluster_kernel, a);
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(a.R * a.heads, a.max_splits);
   cfg.blockDim = dim3(DA_THREADS);
