@@ -88,6 +88,9 @@ VDD_API int vdd_missing_tensors(vdd_engine* e, char* names_out, size_t cap);
  * pixels bf16 [B,3,S,S] -> engine-held image features [B, P, H] fp32.  */
 VDD_API int vdd_encode_images(vdd_engine* e, const void* pixels_bf16, int B, void* stream);
 VDD_API const float* vdd_image_features(vdd_engine* e);
+/* The VCD baseline's noised images (`images_cd`, reference vcd_utils/vcd_add_noise.py:3-28, llava_llama.py:170):
+ * encoded into a second feature plane; call after vdd_encode_images with the same B. */
+VDD_API int vdd_encode_images_cd(vdd_engine* e, const void* pixels_bf16, int B, void* stream);
 
 /* Prefill of all streams in one varlen batch (reference vcd_sample.py:106-119,147-185 at step 0 +
  * llava_arch.py:87-204).  ids_host int64 [B,T], each row holding at most one -200 sentinel.
@@ -96,6 +99,9 @@ VDD_API const float* vdd_image_features(vdd_engine* e);
  * vdd_logits().  */
 VDD_API int vdd_prefill(vdd_engine* e, const int64_t* ids_host, int B, int T, int with_images, int use_unk, int use_none,
                 int max_new_tokens, void* stream);
+/* Prefill of the main stream plus the VCD contrast stream (same prompt, images_cd features spliced in): step 0 of
+ * reference vcd_sample.py:148-150,161-169.  Streams: main, cd. */
+VDD_API int vdd_prefill_cd(vdd_engine* e, const int64_t* ids_host, int B, int T, int max_new_tokens, void* stream);
 /* One decode step for all S*B rows: row (s,b) consumes tokens[b].  Leaves logits in vdd_logits(). */
 VDD_API int vdd_decode_step(vdd_engine* e, const int64_t* tokens, void* stream);
 VDD_API float* vdd_logits(vdd_engine* e); /* fp32 [S, B, V] */
@@ -109,6 +115,14 @@ VDD_API int vdd_num_streams(vdd_engine* e);
 VDD_API int vdd_generate(vdd_engine* e, const int64_t* ids_host, int B, int T, const void* pixels_host, int use_unk,
                  int use_none, const vdd_sample_params* params_host, int max_new_tokens, const float* q_exp,
                  float* scores_out, int64_t* tokens_out_host, int* steps_out, void* stream);
+
+/* Same with the VCD contrast stream: pixels_cd_host bf16 [B,3,S,S] (NULL => identical to vdd_generate).  As in the
+ * reference (vcd_sample.py:148-150) only step 0 contrasts against the noised image; from step 1
+ * the contrast logits are the main logits.  Excludes use_unk / use_none. */
+VDD_API int vdd_generate_cd(vdd_engine* e, const int64_t* ids_host, int B, int T, const void* pixels_host,
+                    const void* pixels_cd_host, int use_unk, int use_none, const vdd_sample_params* params_host,
+                    int max_new_tokens, const float* q_exp, float* scores_out, int64_t* tokens_out_host, int* steps_out,
+                    void* stream);
 
 /* Tensor parallel: 128-byte NCCL unique id made on rank 0, then every rank joins. */
 VDD_API int vdd_tp_unique_id(void* id128_host);

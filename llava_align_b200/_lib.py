@@ -44,12 +44,16 @@ SIGNATURES = {
     "vdd_missing_tensors": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
     "vdd_encode_images": (C.c_int, [_P, _P, C.c_int, _P]),
     "vdd_image_features": (_P, [_P]),
+    "vdd_encode_images_cd": (C.c_int, [_P, _P, C.c_int, _P]),
+    "vdd_prefill_cd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vdd_prefill": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vdd_decode_step": (C.c_int, [_P, _P, _P]),
     "vdd_logits": (_P, [_P]),
     "vdd_num_streams": (C.c_int, [_P]),
     "vdd_generate": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.POINTER(vdd_sample_params), C.c_int, _P,
                                _P, _P, C.POINTER(C.c_int), _P]),
+    "vdd_generate_cd": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.POINTER(vdd_sample_params), C.c_int, _P,
+                                  _P, _P, C.POINTER(C.c_int), _P]),
     "vdd_tp_unique_id": (C.c_int, [_P]),
     "vdd_tp_init": (C.c_int, [_P, _P]),
     "vdd_launch_count": (C.c_int64, [_P, C.c_int]),

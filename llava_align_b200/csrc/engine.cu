@@ -121,7 +121,7 @@ struct vdd_engine {
   unsigned long long* d_trace = nullptr;  // VDD_TRACE=1: time stamps of the middle layer's fused chain
   unsigned* d_bar = nullptr;  // grid-barrier counters of the fused projection chains, [layers + 2][4]
   bool prefilled = false;
-  int image_B = 0;
+  int image_B = 0, image_cd_B = 0;
   // decode buffers (views into dec_f32 / dec_bf16)
   float *resid_d = nullptr, *qkv_d = nullptr, *part_o = nullptr, *part_ml = nullptr, *tp_part = nullptr;
   void *attn_d = nullptr, *h_d = nullptr, *xn_d = nullptr;
@@ -433,7 +433,7 @@ static int do_gemm(vdd_engine* e, const void* a, const void* w, int M, int N, in
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ vision
-extern "C" int vdd_encode_images(vdd_engine* e, const void* pixels, int B, void* stream_v) {
+static int encode_images_slot(vdd_engine* e, const void* pixels, int B, int slot, void* stream_v) {
   if (!e || !pixels || B <= 0) return fail(VDD_ERR_ARG, "bad argument");
   if (vdd_missing_tensors(e, nullptr, 0)) {
     char buf[512];
@@ -452,7 +452,13 @@ extern "C" int vdd_encode_images(vdd_engine* e, const void* pixels, int B, void*
                o_h = carve((size_t)Mv * VI * 2), o_pin = carve((size_t)Mp * VH * 2), o_ph = carve((size_t)Mp * H * 2),
                o_idx = carve((size_t)Mp * 4), o_meta = carve((size_t)B * 32);
   RC(ensure(e, e->vis, o));
-  RC(ensure(e, e->img_feats, (size_t)Mp * H * 4));
+  {  // two planes: [0] the real images, [1] the VCD-noised ones (images_cd); growing must keep plane 0
+    const size_t need = (size_t)2 * Mp * H * 4;
+    if (e->img_feats.bytes < need) {
+      if (slot == 1 && e->image_B == B) return fail(VDD_ERR_STATE, "internal: feature buffer too small for the cd plane");
+      RC(ensure(e, e->img_feats, need));
+    }
+  }
   char* base = (char*)e->vis.p;
   void* patches = base + o_patch; float* pout = (float*)(base + o_pout); float* res = (float*)(base + o_res);
   void* xn = base + o_xn; void* qkv = base + o_qkv; void* att = base + o_att; void* hb = base + o_h;
@@ -497,17 +503,36 @@ extern "C" int vdd_encode_images(vdd_engine* e, const void* pixels, int B, void*
   // feature_select('patch') then mm_projector (mlp2x_gelu)
   LK(e, launch_cast_rows_bf16(res, pin, Mp, VH, idx, st));
   RC(do_gemm(e, pin, e->pj_w1, Mp, H, VH, GEMM_OUT_BF16_GELU, e->pj_b1, nullptr, nullptr, ph, H, st));
-  RC(do_gemm(e, ph, e->pj_w2, Mp, H, H, GEMM_OUT_F32, e->pj_b2, nullptr, (float*)e->img_feats.p, nullptr, H, st));
-  e->image_B = B;
+  RC(do_gemm(e, ph, e->pj_w2, Mp, H, H, GEMM_OUT_F32, e->pj_b2, nullptr, (float*)e->img_feats.p + (size_t)slot * Mp * H, nullptr, H, st));
+  if (slot == 0) e->image_B = B; else e->image_cd_B = B;
   return VDD_OK;
+}
+extern "C" int vdd_encode_images(vdd_engine* e, const void* pixels, int B, void* stream_v) {
+  if (e) e->image_cd_B = 0;
+  return encode_images_slot(e, pixels, B, 0, stream_v);
+}
+// images_cd of the VCD baseline (reference vcd_utils/vcd_add_noise.py + llava_llama.py:170): call after vdd_encode_images
+extern "C" int vdd_encode_images_cd(vdd_engine* e, const void* pixels, int B, void* stream_v) {
+  if (!e || e->image_B != B) return fail(VDD_ERR_STATE, "vdd_encode_images(B=%d) must precede vdd_encode_images_cd", B);
+  return encode_images_slot(e, pixels, B, 1, stream_v);
 }
 extern "C" const float* vdd_image_features(vdd_engine* e) { return e ? (const float*)e->img_feats.p : nullptr; }
 
 // ------------------------------------------------------------------------------------------------ prefill
 static int tp_gather_logits(vdd_engine* e, cudaStream_t st);
 
+static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int with_images, int use_unk, int use_none, int use_cd,
+                        int max_new, void* stream_v);
 extern "C" int vdd_prefill(vdd_engine* e, const int64_t* ids, int B, int T, int with_images, int use_unk, int use_none,
                            int max_new, void* stream_v) {
+  return prefill_impl(e, ids, B, T, with_images, use_unk, use_none, 0, max_new, stream_v);
+}
+// main + VCD contrast stream (the same prompt with images_cd spliced in; reference vcd_sample.py:148-150 at step 0)
+extern "C" int vdd_prefill_cd(vdd_engine* e, const int64_t* ids, int B, int T, int max_new, void* stream_v) {
+  return prefill_impl(e, ids, B, T, 1, 0, 0, 1, max_new, stream_v);
+}
+static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int with_images, int use_unk, int use_none, int use_cd,
+                        int max_new, void* stream_v) {
   if (!e || !ids || B <= 0 || T <= 0 || max_new < 1) return fail(VDD_ERR_ARG, "bad argument");
   if (vdd_missing_tensors(e, nullptr, 0)) {
     char buf[512];
@@ -517,12 +542,14 @@ extern "C" int vdd_prefill(vdd_engine* e, const int64_t* ids, int B, int T, int 
   cudaStream_t st = (cudaStream_t)stream_v;
   const vdd_config& c = e->c;
   const int H = c.hidden_size, NP = e->NP, L = c.num_layers, Hl = e->Hl, Il = e->Il;
-  const int S = 1 + (use_unk ? 1 : 0) + (use_none ? 1 : 0), R = S * B;
+  const int S = 1 + (use_unk ? 1 : 0) + (use_none ? 1 : 0) + (use_cd ? 1 : 0), R = S * B;
+  if (use_cd && e->image_cd_B != B) return fail(VDD_ERR_STATE, "vdd_encode_images_cd(B=%d) must precede the cd prefill", B);
   if (with_images && e->image_B != B) return fail(VDD_ERR_STATE, "vdd_encode_images(B=%d) must precede prefill(B=%d)", e->image_B, B);
 
   // ---- row plan (vcd_sample.py:152-160: unk = sentinel -> token 0; none = sentinel deleted; main = 576 image rows)
-  std::vector<int> kinds;  // 0 main, 1 unk, 2 none
+  std::vector<int> kinds;  // 0 main, 1 unk, 2 none, 3 cd (main prompt with the noised image's features)
   kinds.push_back(0);
+  if (use_cd) kinds.push_back(3);
   if (use_unk) kinds.push_back(1);
   if (use_none) kinds.push_back(2);
   std::vector<int32_t> tok, img_row, row_seq, row_pos, seqlen(R), q_row0(R), kv_cap(R), last_rows(R);
@@ -539,10 +566,11 @@ extern "C" int vdd_prefill(vdd_engine* e, const int64_t* ids, int B, int T, int 
         if (id == VDD_IMAGE_TOKEN_INDEX) {
           ++nsent;
           if (nsent > 1) return fail(VDD_ERR_UNSUPPORTED, "row %d holds more than one image sentinel", b);
-          if (kinds[s] == 0) {
+          if (kinds[s] == 0 || kinds[s] == 3) {
             if (!with_images) return fail(VDD_ERR_ARG, "row %d has an image sentinel but no images were given", b);
+            const int plane = kinds[s] == 3 ? B * NP : 0;
             for (int p = 0; p < NP; ++p) {
-              tok.push_back(-1); img_row.push_back(b * NP + p); row_seq.push_back(q); row_pos.push_back(pos++);
+              tok.push_back(-1); img_row.push_back(plane + b * NP + p); row_seq.push_back(q); row_pos.push_back(pos++);
             }
           } else if (kinds[s] == 1) {
             tok.push_back(0); img_row.push_back(-1); row_seq.push_back(q); row_pos.push_back(pos++);
@@ -826,37 +854,52 @@ extern "C" int vdd_logit_combine_sample(const float* l, const float* u, const fl
 }
 
 // ------------------------------------------------------------------------------------------------ generate
+static int upload_and_encode(vdd_engine* e, const void* pixels, int B, int slot, cudaStream_t st) {
+  const vdd_config& c = e->c;
+  const size_t nb = (size_t)B * 3 * c.image_size * c.image_size * 2;
+  cudaPointerAttributes pa{};
+  const bool on_device = cudaPointerGetAttributes(&pa, pixels) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  if (on_device) return encode_images_slot(e, pixels, B, slot, st);  // already resident (bench.py's device-only leg)
+  RC(ensure(e, e->pix, nb));
+  CK(cudaMemcpyAsync(e->pix.p, pixels, nb, cudaMemcpyHostToDevice, st));
+  return encode_images_slot(e, e->pix.p, B, slot, st);
+}
+
 extern "C" int vdd_generate(vdd_engine* e, const int64_t* ids, int B, int T, const void* pixels_host, int use_unk, int use_none,
                             const vdd_sample_params* p, int max_new, const float* q_exp, float* scores_out,
                             int64_t* tokens_out_host, int* steps_out, void* stream_v) {
+  return vdd_generate_cd(e, ids, B, T, pixels_host, nullptr, use_unk, use_none, p, max_new, q_exp, scores_out, tokens_out_host,
+                         steps_out, stream_v);
+}
+
+extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, const void* pixels_host, const void* pixels_cd_host,
+                               int use_unk, int use_none, const vdd_sample_params* p, int max_new, const float* q_exp,
+                               float* scores_out, int64_t* tokens_out_host, int* steps_out, void* stream_v) {
   if (!e || !ids || !p || !tokens_out_host || max_new < 1) return fail(VDD_ERR_ARG, "bad argument");
   if (e->c.vocab_size > 32768) return fail(VDD_ERR_UNSUPPORTED, "vocab > 32768");
   if (!(p->temperature > 0.f)) return fail(VDD_ERR_ARG, "temperature must be > 0");
   cudaStream_t st = (cudaStream_t)stream_v;
   const vdd_config& c = e->c;
   CK(cudaEventRecord(e->ev[0], st));
+  const bool use_cd = pixels_cd_host != nullptr;
+  if (use_cd && (!pixels_host || use_unk || use_none))
+    return fail(VDD_ERR_UNSUPPORTED, "images_cd needs images and excludes use_dd / use_dd_unk in this build");
   if (pixels_host) {
-    const size_t nb = (size_t)B * 3 * c.image_size * c.image_size * 2;
-    cudaPointerAttributes pa{};
-    const bool on_device = cudaPointerGetAttributes(&pa, pixels_host) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
-    cudaGetLastError();
-    if (on_device) {  // already resident (bench.py's device-only leg)
-      RC(vdd_encode_images(e, pixels_host, B, st));
-    } else {
-      RC(ensure(e, e->pix, nb));
-      CK(cudaMemcpyAsync(e->pix.p, pixels_host, nb, cudaMemcpyHostToDevice, st));
-      RC(vdd_encode_images(e, e->pix.p, B, st));
-    }
+    e->image_cd_B = 0;
+    RC(upload_and_encode(e, pixels_host, B, 0, st));
+    if (use_cd) RC(upload_and_encode(e, pixels_cd_host, B, 1, st));
   }
   CK(cudaEventRecord(e->ev[1], st));
-  RC(vdd_prefill(e, ids, B, T, pixels_host != nullptr, use_unk, use_none, max_new, st));
-  const int V = c.vocab_size, S = e->S;
+  RC(prefill_impl(e, ids, B, T, pixels_host != nullptr, use_unk, use_none, use_cd ? 1 : 0, max_new, st));
+  const int V = c.vocab_size;
+  int S = e->S;
   // device-resident sampler arguments: the graph reads them through a pointer, so one graph serves every call
   SampleArgs a{};
   float* lg = (float*)e->logits.p;
   a.l = lg;
   int si = 1;
-  a.u = use_unk ? lg + (size_t)(si++) * B * V : nullptr;
+  a.u = (use_unk || use_cd) ? lg + (size_t)(si++) * B * V : nullptr;
   a.d = use_none ? lg + (size_t)(si++) * B * V : nullptr;
   a.q = q_exp; a.scores_out = scores_out; a.tokens_out = e->d_tokens; a.seq_out = e->d_seq_out; a.seq_ld = max_new;
   a.unfinished = e->d_unfinished; a.step_ptr = e->d_step; a.ld = V; a.B = B; a.V = V;
@@ -874,13 +917,24 @@ extern "C" int vdd_generate(vdd_engine* e, const int64_t* ids, int B, int T, con
   CK(cudaMemcpyAsync(e->d_unfinished, h_unf, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   LK(e, launch_combine_sample(a, e->d_sargs, B, V, st));  // step 0 on the prefill logits
   LK(e, launch_advance(nullptr, 0, e->d_step, st));  // step = 1
+  if (use_cd) {
+    // reference vcd_sample.py:148-150: model_kwargs_cd is re-copied from the MAIN stream's kwargs every step, so from
+    // step 1 on the "contrast" forward runs on the main KV cache and its logits equal the main logits (SURVEY Appendix A
+    // Q7).  The cd rows are therefore dropped after step 0 and the combine reads l as its own contrast.
+    CK(cudaStreamSynchronize(st));
+    e->S = 1;
+    e->R = B;
+    S = 1;
+    a.u = a.l;
+    memcpy(e->pinned, &a, sizeof a);
+    CK(cudaMemcpyAsync(e->d_sargs, e->pinned, sizeof a, cudaMemcpyHostToDevice, st));
+  }
   CK(cudaEventRecord(e->ev[2], st));
 
   int steps = 1;
   if (max_new > 1) {
     const uint64_t key = ((uint64_t)B << 40) ^ ((uint64_t)S << 32) ^ ((uint64_t)e->max_splits << 16) ^ (uint64_t)(e->use_pdl ? 1 : 0) ^ (uint64_t)(e->use_fused ? 2 : 0) ^
                          (uint64_t)((a.top_p < 1.0f || (a.top_k > 1 && a.top_k < V)) ? 4 : 0) ^  // which K8 kernel the graph holds
-                        
                          ((uint64_t)(uintptr_t)e->kv.p << 1) ^ (uint64_t)(uintptr_t)e->logits.p ^ ((uint64_t)e->kv_layer_stride << 3);
     int per_step_launches = 0;
     const bool graph = e->use_graph && st != nullptr;  // the legacy default stream cannot be captured

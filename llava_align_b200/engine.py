@@ -178,20 +178,23 @@ class VddEngine:
     # ---- fused generate (the product path): host buffers in, host tokens out
     def generate(self, input_ids: torch.Tensor, images: Optional[torch.Tensor], use_unk: bool, use_none: bool,
                  params: _lib.vdd_sample_params, max_new_tokens: int, q: Optional[torch.Tensor] = None,
-                 scores_out: Optional[torch.Tensor] = None):
+                 scores_out: Optional[torch.Tensor] = None, images_cd: Optional[torch.Tensor] = None):
         ids = input_ids.detach().to("cpu", torch.int64).contiguous()
         B, T = ids.shape
         px = None
         if images is not None:
             # host (ideally pinned) pixels are copied by the library inside the call; device pixels are used in place
             px = images.detach().to(torch.bfloat16).contiguous()
+        pxc = None
+        if images_cd is not None:
+            pxc = images_cd.detach().to(torch.bfloat16).contiguous()
         out = torch.empty(B, max_new_tokens, dtype=torch.int64).pin_memory()
         steps = C.c_int(0)
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         self.stream.wait_stream(torch.cuda.current_stream(self.device))  # q / scores_out were produced there
-        _lib.check(self.lib.vdd_generate(self.h, ptr(ids), B, T, ptr(px), int(use_unk), int(use_none), C.byref(params),
-                                         int(max_new_tokens), ptr(q), ptr(scores_out), ptr(out), C.byref(steps),
-                                         C.c_void_p(self.stream.cuda_stream)), "vdd_generate")  # returns synchronised
+        _lib.check(self.lib.vdd_generate_cd(self.h, ptr(ids), B, T, ptr(px), ptr(pxc), int(use_unk), int(use_none),
+                                            C.byref(params), int(max_new_tokens), ptr(q), ptr(scores_out), ptr(out),
+                                            C.byref(steps), C.c_void_p(self.stream.cuda_stream)), "vdd_generate")  # synchronised
         self._B = B
         return out[:, :steps.value], steps.value
 

@@ -106,8 +106,6 @@ class LlavaLlamaForCausalLM:
             raise ValueError(f"The following `model_kwargs` are not used by the model: {sorted(kwargs)}")  # HF _validate_model_kwargs
         if num_beams != 1:
             raise NotImplementedError("beam search is outside the VDD path (reference scripts use num_beams=1)")
-        if images_cd is not None:
-            raise NotImplementedError("use_cd (VCD noise stream, images_cd) is a 'next' row of the scope table, not built yet")
         if input_ids.dim() == 1:
             input_ids = input_ids.unsqueeze(0)
         B, T = input_ids.shape
@@ -128,7 +126,11 @@ class LlavaLlamaForCausalLM:
 
         has_image = images is not None and bool((input_ids == IMAGE_TOKEN_INDEX).any())
         do_sample = bool(opt["do_sample"])
-        vdd = do_sample and vdd_sampler_installed() and bool(use_dd or use_dd_unk)
+        # VDD/VCD is active iff images_cd is given or use_dd / use_dd_unk is set (vcd_sample.py:122-124,147)
+        use_cd = images_cd is not None and has_image
+        vdd = do_sample and vdd_sampler_installed() and bool(use_dd or use_dd_unk or use_cd)
+        if vdd and use_cd and (use_dd or use_dd_unk):
+            raise NotImplementedError("images_cd together with use_dd/use_dd_unk (vcd_sample.py:148,171-185) is not built")
         use_unk = bool(vdd and use_dd_unk)
         use_none = bool(vdd and use_dd)
         if do_sample:
@@ -149,7 +151,7 @@ class LlavaLlamaForCausalLM:
         want_scores = bool(opt["output_scores"] and opt["return_dict_in_generate"])
         scores_buf = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device) if want_scores else None
         new_tokens, steps = self.engine.generate(input_ids, images if has_image else None, use_unk, use_none, params,
-                                                 max_new_tokens, q, scores_buf)
+                                                 max_new_tokens, q, scores_buf, images_cd if (vdd and use_cd) else None)
         seq = torch.cat([input_ids.to("cpu", torch.int64), new_tokens], dim=1).to(input_ids.device)
         if not opt["return_dict_in_generate"]:
             return seq

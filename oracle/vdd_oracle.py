@@ -211,7 +211,7 @@ class OracleVDD:
         return out.logits[:, -1, :].float(), cache  # vcd_sample.py:119 (last position only)
 
     @torch.no_grad()
-    def generate(self, input_ids, images=None, use_dd=False, use_dd_unk=False, cd_alpha=None, cd_beta=None,
+    def generate(self, input_ids, images=None, images_cd=None, use_dd=False, use_dd_unk=False, cd_alpha=None, cd_beta=None,
                  temperature=None, top_k=None, top_p=None, max_new_tokens=16, do_sample=True,
                  output_scores=False, keep_stream_logits=False, q_list=None, eos_token_id="cfg",
                  pad_token_id=None):
@@ -229,8 +229,14 @@ class OracleVDD:
             main_embeds = splice_main(embed, input_ids, feats.to(self.dtype))
         else:
             main_embeds = None
+        cd_embeds = None
+        if images_cd is not None and images is not None:
+            # use_cd (vcd_sample.py:122,148-150): the contrast forward sees the same prompt with images_cd spliced in
+            assert not (use_dd or use_dd_unk), "restated for use_cd alone"
+            feats_cd = encode_images(self.vision, self.projector, images_cd, cfg.mm_vision_select_layer)
+            cd_embeds = splice_main(embed, input_ids, feats_cd.to(self.dtype))
         t["vision_s"] = time.perf_counter() - t0
-        vdd = bool(use_dd or use_dd_unk) and do_sample  # do_sample=False bypasses the patched sampler (Q9)
+        vdd = bool(use_dd or use_dd_unk or cd_embeds is not None) and do_sample  # do_sample=False bypasses the patched sampler (Q9)
         unfinished = torch.ones(B, dtype=torch.long)
         caches = {"m": None, "u": None, "d": None}
         seq = input_ids.clone()
@@ -250,7 +256,14 @@ class OracleVDD:
             else:
                 l, caches["m"] = self._forward(caches["m"], input_ids=last_tok)
             u = d = None
-            if vdd:
+            if vdd and cd_embeds is not None:
+                # model_kwargs_cd = model_kwargs.copy() EVERY step (vcd_sample.py:149): from step 1 on it carries the main
+                # stream's cache, so the contrast forward is the main forward again (Appendix A Q7)
+                if first:
+                    u, _ = self._forward(None, inputs_embeds=cd_embeds)
+                else:
+                    u = l.clone()
+            elif vdd:
                 # vcd_sample.py:151-169: the first contrast stream is 'unk' when use_dd_unk is set, else 'none'
                 if use_dd_unk:
                     u, caches["u"] = self._forward(caches["u"], input_ids=debias_ids(seq, "unk") if first else last_tok)

@@ -15,6 +15,10 @@ Shims (the reference targets transformers 4.31; 5.5.0 is installed here) -- name
   * AutoConfig.register('llava') is a no-op (transformers 5.5 already owns a 'llava' model type)
   * DynamicCache.__getitem__ -> (keys, values) of a layer, for the tuple-cache indexing at llava_arch.py:93
   * a 4.31-style max-length stopping criterion returning a python bool (vcd_sample.py:295)
+  * the model's forward deep-copies `past_key_values` on entry: transformers-4.31 caches are immutable tuples (every
+    forward returns NEW tensors via torch.cat), 5.5's DynamicCache is updated in place.  The reference relies on the
+    former when it hands the main stream's cache to the use_cd contrast forward (`model_kwargs.copy()` every step,
+    vcd_sample.py:148-150); without the copy that forward would append the token to the main cache a second time.
 `sample()` is called directly the way transformers-4.31 `generate()` calls it: logits_warper built in
 _get_logits_warper order (Temperature, TopK, TopP), MaxLengthCriteria, attention_mask of ones, and the
 drivers' kwargs (images, use_dd, use_dd_unk, cd_alpha, cd_beta, use_cache) as model_kwargs.
@@ -104,6 +108,15 @@ def build_reference_model(ref_llama, cfg, sd):
     res = model.load_state_dict(sd, strict=False)
     bad = [k for k in res.missing_keys if "rotary" not in k and "position_ids" not in k]
     assert not bad and not res.unexpected_keys, (bad, res.unexpected_keys)
+    import copy
+    orig_forward = model.forward
+
+    def forward_431(*a, **k):  # immutable-cache semantics of transformers 4.31 (see the module docstring)
+        if k.get("past_key_values") is not None:
+            k["past_key_values"] = copy.deepcopy(k["past_key_values"])
+        return orig_forward(*a, **k)
+
+    model.forward = forward_431
     return model
 
 
@@ -118,7 +131,7 @@ def make_inputs(cfg, B, T, seed):
     return torch.from_numpy(ids), img
 
 
-def run_reference(ref_sample, model, ids, img, n_new, flags, sampler, eos, seed):
+def run_reference(ref_sample, model, ids, img, n_new, flags, sampler, eos, seed, img_cd=None):
     from transformers.generation.logits_process import (LogitsProcessorList, TemperatureLogitsWarper,
                                                         TopKLogitsWarper, TopPLogitsWarper)
 
@@ -146,7 +159,7 @@ def run_reference(ref_sample, model, ids, img, n_new, flags, sampler, eos, seed)
             model, ids.clone(), logits_warper=warpers,
             stopping_criteria=MaxLength431(ids.shape[1] + n_new),
             pad_token_id=model.config.pad_token_id, eos_token_id=eos, output_scores=True,
-            return_dict_in_generate=True, attention_mask=torch.ones_like(ids), images=img, images_cd=None,
+            return_dict_in_generate=True, attention_mask=torch.ones_like(ids), images=img, images_cd=img_cd,
             use_cache=True, **flags)
     return out.sequences, torch.stack(out.scores, dim=0)  # [B,T+n], [n,B,V]
 
@@ -163,6 +176,9 @@ CASES = [
     ("plain_sample_t1", 1, 12, 8, dict(use_dd=False, use_dd_unk=False), dict(top_p=0.8, top_k=50), None),
     ("unk_batch2_greedy", 2, 12, 8, dict(use_dd=False, use_dd_unk=True, cd_alpha=1.0, cd_beta=0.1), dict(top_k=1), None),
     ("unk_batch2_eos", 2, 12, 8, dict(use_dd=False, use_dd_unk=True, cd_alpha=1.0, cd_beta=0.1), dict(top_k=1), "auto"),
+    # use_cd: images_cd = add_diffusion_noise(image, 500) (vcd_utils/vcd_add_noise.py), VCD baseline of the reference
+    ("cd_greedy", 1, 12, 8, dict(use_dd=False, use_dd_unk=False, cd_alpha=1.0, cd_beta=0.1, use_cd=500), dict(top_k=1), None),
+    ("cd_sample_batch2", 2, 12, 8, dict(use_dd=False, use_dd_unk=False, cd_alpha=0.5, cd_beta=0.2, use_cd=700), dict(top_p=0.9), None),
 ]
 
 
@@ -177,14 +193,22 @@ def main():
     meta = []
     for i, (name, B, T, n_new, flags, sampler, eos) in enumerate(CASES):
         ids, img = make_inputs(cfg, B, T, seed=100 + i)
+        flags = dict(flags)
+        img_cd = None
+        if flags.get("use_cd"):
+            sys.path.insert(0, REF)
+            from vcd_utils.vcd_add_noise import add_diffusion_noise  # the reference's own noising, unmodified
+            torch.manual_seed(1000 + i)
+            img_cd = add_diffusion_noise(img, flags.pop("use_cd")).to(torch.bfloat16).float()
+            out[f"{name}.images_cd"] = img_cd.numpy()
         if eos == "auto":
             # pick the token row 0 emits at step 2 as EOS so rows finish at different steps
             seq0, _ = run_reference(ref_sample, model, ids, img, n_new, flags, sampler, None, seed=7)
             eos = int(seq0[0, T + 2])
-        seq, scores = run_reference(ref_sample, model, ids, img, n_new, flags, sampler, eos, seed=7)
+        seq, scores = run_reference(ref_sample, model, ids, img, n_new, flags, sampler, eos, seed=7, img_cd=img_cd)
         out[f"{name}.sequences"] = seq.numpy()
         out[f"{name}.scores"] = scores.float().numpy()
-        meta.append(dict(name=name, B=B, T=T, n_new=n_new, flags=flags, sampler=sampler, eos=eos,
+        meta.append(dict(name=name, B=B, T=T, n_new=n_new, flags=dict(flags, use_cd=img_cd is not None), sampler=sampler, eos=eos,
                          input_seed=100 + i, sample_seed=7))
         print(name, seq[:, T:].tolist())
     import json

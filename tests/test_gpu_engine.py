@@ -75,7 +75,7 @@ def test_generate_matches_reference_golden(engine_model, case):
     params = E.make_sample_params(cd_alpha=0.5 if f.get("cd_alpha") is None else f["cd_alpha"],
                                   cd_beta=0.1 if f.get("cd_beta") is None else f["cd_beta"],
                                   temperature=s.get("temperature"), top_k=s.get("top_k"), top_p=s.get("top_p"),
-                                  use_contrast=bool(f.get("use_dd") or f.get("use_dd_unk")), eos_token_id=case["eos"],
+                                  use_contrast=bool(f.get("use_dd") or f.get("use_dd_unk") or f.get("use_cd")), eos_token_id=case["eos"],
                                   pad_token_id=cfg.pad_token_id)
     q = None
     if not greedy:
@@ -83,7 +83,8 @@ def test_generate_matches_reference_golden(engine_model, case):
         torch.manual_seed(case["sample_seed"])
         q = torch.stack([torch.empty(B, V).exponential_(1) for _ in range(n)]).cuda()
     scores = torch.empty(n, B, V, device="cuda")
-    toks, steps = m.engine.generate(ids, img, bool(f.get("use_dd_unk")), bool(f.get("use_dd")), params, n, q, scores)
+    img_cd = torch.from_numpy(DATA[case["name"] + ".images_cd"]) if f.get("use_cd") else None
+    toks, steps = m.engine.generate(ids, img, bool(f.get("use_dd_unk")), bool(f.get("use_dd")), params, n, q, scores, img_cd)
     assert steps == ref_seq.shape[1] - case["T"]
     got_scores = scores[:steps].cpu()
     # step 0 is free of feedback: sets and values must agree within the logit tolerance
@@ -131,3 +132,7 @@ def test_generate_surface(engine_model):
     assert r["sequences"].shape == (1, 17) and len(r["scores"]) == 5 and r["scores"][0].shape == (1, cfg.vocab_size)
     with pytest.raises(ValueError):
         m.generate(ids.cuda(), images=img.cuda(), bogus_kwarg=1, max_new_tokens=2)
+    # use_cd: images_cd alone switches the contrast on (vcd_sample.py:122,147); identical images => (1+a)l - a*l with the cutoff
+    c1 = m.generate(ids.cuda(), images=img.cuda(), images_cd=(img + 0.5 * torch.randn_like(img)).cuda(), cd_alpha=1.0, cd_beta=0.1,
+                    do_sample=True, top_k=1, max_new_tokens=5, eos_token_id=None)
+    assert c1.shape == (1, 17) and torch.equal(c1[:, :12].cpu(), ids)

@@ -15,7 +15,8 @@ def test_oracle_matches_reference(case):
     ids, img = make_inputs(cfg, case["B"], case["T"], case["input_seed"])
     f, s = case["flags"], case["sampler"]
     torch.manual_seed(case["sample_seed"])  # the reference draws from the global generator (torch.multinomial)
-    out = oracle.generate(ids, img, use_dd=f.get("use_dd", False), use_dd_unk=f.get("use_dd_unk", False),
+    img_cd = torch.from_numpy(DATA[case["name"] + ".images_cd"]) if f.get("use_cd") else None
+    out = oracle.generate(ids, img, images_cd=img_cd, use_dd=f.get("use_dd", False), use_dd_unk=f.get("use_dd_unk", False),
                           cd_alpha=f.get("cd_alpha"), cd_beta=f.get("cd_beta"),
                           temperature=s.get("temperature"), top_k=s.get("top_k"), top_p=s.get("top_p"),
                           max_new_tokens=case["n_new"], output_scores=True, eos_token_id=case["eos"])
