@@ -5,7 +5,7 @@
 // triggers from llava_llama.py:91-103, clip_encoder.py:48 and llava_arch.py:84.
 //
 // sm_100a design: one 128x128 output tile per CTA; operands arrive by TMA (cp.async.bulk.tensor, 128B swizzle,
-// out-of-bounds rows/columns zero-filled so M, N, K need not be tile multiples) into a 4-stage shared-memory ring
+// out-of-bounds rows/columns zero-filled so M, N, K need not be tile multiples) into a 3-stage shared-memory ring
 // guarded by full/empty mbarriers; ONE thread issues tcgen05.mma (UMMA 128x128x16, kind::f16, bf16 inputs) with the
 // fp32 accumulator in 128 TMEM columns; tcgen05.commit releases ring slots and finally signals the epilogue warps,
 // which read TMEM with tcgen05.ld (32 lanes x 16 columns) and apply the fused epilogue (bias, quick_gelu / gelu,
@@ -18,7 +18,7 @@
 
 namespace vdd {
 
-constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 64, GM_STAGES = 4;
+constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 64, GM_STAGES = 3;  // 3 x 32 KB per CTA => two CTAs per SM: one's epilogue overlaps the other's main loop
 constexpr int GM_THREADS = 192;
 constexpr int GM_STAGE_BYTES = (GM_BM + GM_BN) * GM_BK * 2;  // 32 KB
 constexpr int GM_SMEM = GM_STAGES * GM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -35,7 +35,7 @@ struct GemmEpi {
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + expf(-1.702f * x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-__global__ void __launch_bounds__(GM_THREADS, 1)
+__global__ void __launch_bounds__(GM_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmEpi ep) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
