@@ -146,7 +146,7 @@ def workload_config(a, cfg, n, mode="dp"):
                         f"(3 fused streams), cd_alpha=1 cd_beta=0.1, temperature-1 sampling, EOS disabled",
             "global_batch": a.batch, "new_tokens": a.new_tokens, "prompt_len": a.prompt_len, "streams": 3,
             "parallelism": "single GPU" if n == 1 else (
-                f"tp{n} (heads/FFN/vocab split, NCCL all-reduce after o_proj/down_proj, all-gather of the vocab shards)" if mode == "tp"
+                f"tp{n} (heads/FFN/vocab split; decode: all-reduce and logit all-gather inside the projection kernel over NVLink peer memory; prefill: NCCL)" if mode == "tp"
                 else f"dp{n}: {n} independent replicas, one request stream per GPU, no data-path collective"),
             "l2_policy": "inputs larger than L2: every step streams the 13.2 GB of weights (L2 = 126 MB); no flush needed"}
 
@@ -196,11 +196,7 @@ def main():
                                              tp_rank=rank if tp > 1 else 0)
     eng = model.engine
     if tp > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            idt = torch.frombuffer(bytearray(E.VddEngine.tp_unique_id()), dtype=torch.uint8).to(dev)
-        dist.broadcast(idt, 0)
-        eng.tp_init(bytes(idt.cpu().numpy().tobytes()))
+        eng.tp_setup(dist)
     B, T, n_new = a.batch, a.prompt_len, a.new_tokens
     ids, img = synthetic_inputs(cfg, B, T)
     img_pinned = img.pin_memory()

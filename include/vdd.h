@@ -127,6 +127,11 @@ VDD_API int vdd_generate_cd(vdd_engine* e, const int64_t* ids_host, int B, int T
 /* Tensor parallel: 128-byte NCCL unique id made on rank 0, then every rank joins. */
 VDD_API int vdd_tp_unique_id(void* id128_host);
 VDD_API int vdd_tp_init(vdd_engine* e, const void* id128_host);
+/* In-kernel all-reduce over NVLink peer memory (decode with <= 8 fused rows): every rank exports its 64-byte cudaIpc
+ * handle, the host gathers them ([tp][64], rank order) and every rank maps its peers.  Without these two calls tensor
+ * parallel decode falls back to NCCL all-reduce launches. */
+VDD_API int vdd_tp_comm_handle(vdd_engine* e, void* handle64_host);
+VDD_API int vdd_tp_comm_open(vdd_engine* e, const void* handles_host);
 
 /* Introspection for bench.py: kernels launched since the last reset; per-phase device times of the last generate. */
 VDD_API int64_t vdd_launch_count(vdd_engine* e, int reset);

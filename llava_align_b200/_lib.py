@@ -56,6 +56,8 @@ SIGNATURES = {
                                   _P, _P, C.POINTER(C.c_int), _P]),
     "vdd_tp_unique_id": (C.c_int, [_P]),
     "vdd_tp_init": (C.c_int, [_P, _P]),
+    "vdd_tp_comm_handle": (C.c_int, [_P, _P]),
+    "vdd_tp_comm_open": (C.c_int, [_P, _P]),
     "vdd_launch_count": (C.c_int64, [_P, C.c_int]),
     "vdd_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "vdd_bench_projection_chain": (C.c_int, [_P, _P]),

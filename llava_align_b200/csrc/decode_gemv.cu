@@ -105,6 +105,34 @@ __device__ __forceinline__ void grid_wait(const unsigned* counter, unsigned targ
   __syncthreads();
 }
 
+// ---- cross-GPU barrier over peer memory (tensor parallel): every CTA of every rank bumps the counter on EVERY rank
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tp_arrive(const TpComm& t, int cidx) {
+  __syncthreads();  // every thread's peer stores of this phase are issued
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int k = 0; k < t.tp; ++k) {
+      unsigned* c = reinterpret_cast<unsigned*>(t.peers[k]) + cidx;
+      asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void tp_wait(const TpComm& t, int cidx, unsigned target) {
+  if (threadIdx.x == 0) {
+    const unsigned* c = reinterpret_cast<const unsigned*>(t.peers[t.rank]) + cidx;
+    unsigned spins = 0;
+    while (ld_acquire_sys_u32(c) < target) {
+      if (++spins > (1u << 23)) __trap();
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -217,7 +245,7 @@ __device__ __forceinline__ void phase_begin(const GemvArgs& a, GemvCtx& c) {
 // around ONE copy of the stream loop (a fused chain runs four projections through the same instructions).
 template <int R>
 __device__ __forceinline__ void phase_rest(const GemvArgs& a, GemvCtx& c, unsigned char* smem, float* red,
-                                           unsigned long long* trace, int ph) {
+                                           unsigned long long* trace, int ph, const TpComm& tpc) {
   const int K = a.K;
   const int XS = K + GV_XPAD;  // x row stride (elements)
   const int nthreads = blockDim.x;
@@ -384,9 +412,18 @@ __device__ __forceinline__ void phase_rest(const GemvArgs& a, GemvCtx& c, unsign
       float s = 0.f;
       for (int q = 0; q < p.ks; ++q) s += part[((size_t)row * p.ks + q) * R + r];
       GV_TRACE(7);
-      float* o = a.out_f32 + (size_t)r * a.ld_out + p.n0 + row;
-      if (epi == GEMV_OUT_ADD_RESID) *o = (i < nthreads ? resid_old : __ldcg(o)) + s;
-      else *o = s;
+      if (epi == GEMV_OUT_TP_PARTIAL) {
+        // this rank's K-slice of the projection: hand the partial to every rank (its own inbox plane included)
+        const size_t idx = ((size_t)(a.tp_slot * tpc.tp + tpc.rank) * 8 + r) * tpc.H + p.n0 + row;
+        for (int k = 0; k < tpc.tp; ++k) reinterpret_cast<float*>(tpc.peers[k] + tpc.off_inbox)[idx] = s;
+      } else if (epi == GEMV_OUT_TP_LOGITS) {
+        const size_t idx = (size_t)r * tpc.V + (size_t)tpc.rank * tpc.Vl + p.n0 + row;
+        for (int k = 0; k < tpc.tp; ++k) reinterpret_cast<float*>(tpc.peers[k] + tpc.off_logits)[idx] = s;
+      } else {
+        float* o = a.out_f32 + (size_t)r * a.ld_out + p.n0 + row;
+        if (epi == GEMV_OUT_ADD_RESID) *o = (i < nthreads ? resid_old : __ldcg(o)) + s;
+        else *o = s;
+      }
     }
   }
 }
@@ -425,12 +462,37 @@ __global__ void __launch_bounds__(GV_MAX_WARPS * 32, 1) gemv_kernel(const GemvCh
   for (int ph = 0; ph < ch.n; ++ph) {
     const GemvArgs& a = ch.ph[ph];
     GV_TRACE(1);
-    phase_rest<R>(a, c, smem, red, trace, ph);
+    phase_rest<R>(a, c, smem, red, trace, ph, ch.tpc);
     GV_TRACE(5);
+    const bool tp_epi = a.epilogue == GEMV_OUT_TP_PARTIAL || a.epilogue == GEMV_OUT_TP_LOGITS;
+    const unsigned tp_target = tp_epi ? (unsigned)(*ch.tpc.epoch + 1) * (unsigned)ch.tpc.tp * gridDim.x : 0u;
+    if (tp_epi) tp_arrive(ch.tpc, a.tp_counter);
     if (ph + 1 < ch.n) {
-      grid_arrive(ch.barrier + ph);
-      phase_begin(ch.ph[ph + 1], c);  // the next projection's weights start flowing while we wait for the other CTAs
-      grid_wait(ch.barrier + ph, gridDim.x);
+      if (a.epilogue == GEMV_OUT_TP_PARTIAL) {
+        // all-reduce fused into the chain: (1) every rank's partials are in every inbox once the cross-GPU counter is
+        // full, (2) each CTA sums ITS band over the source ranks in rank order into the replicated residual, (3) a
+        // local grid barrier publishes the residual to the next projection's RMSNorm.
+        const int bn0 = c.p.n0, bn1 = c.p.n1;
+        phase_begin(ch.ph[ph + 1], c);  // next weights are requested before any waiting
+        tp_wait(ch.tpc, a.tp_counter, tp_target);
+        const float* inbox = reinterpret_cast<const float*>(ch.tpc.peers[ch.tpc.rank] + ch.tpc.off_inbox);
+        for (int i = threadIdx.x; i < (bn1 - bn0) * R; i += blockDim.x) {
+          const int row = i / R, r = i - row * R;
+          float* o = a.out_f32 + (size_t)r * a.ld_out + bn0 + row;
+          float v = __ldcg(o);
+          for (int k = 0; k < ch.tpc.tp; ++k)
+            v += __ldcg(inbox + ((size_t)(a.tp_slot * ch.tpc.tp + k) * 8 + r) * ch.tpc.H + bn0 + row);
+          *o = v;
+        }
+        grid_arrive(ch.barrier + ph);
+        grid_wait(ch.barrier + ph, gridDim.x);
+      } else {
+        grid_arrive(ch.barrier + ph);
+        phase_begin(ch.ph[ph + 1], c);  // the next projection's weights start flowing while we wait for the other CTAs
+        grid_wait(ch.barrier + ph, gridDim.x);
+      }
+    } else if (tp_epi) {
+      tp_wait(ch.tpc, a.tp_counter, tp_target);  // the kernel ends only when every rank's contribution has landed here
     }
   }
 }
@@ -456,6 +518,8 @@ cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaSt
     const GemvArgs& a = ch.ph[i];
     if (a.R != R || a.R < 1 || a.R > 8 || (a.K % 8) != 0 || (a.N % 2) != 0) return cudaErrorInvalidValue;
     if (a.x_resid && a.epilogue == GEMV_OUT_ADD_RESID) return cudaErrorInvalidValue;
+    if ((a.epilogue == GEMV_OUT_TP_PARTIAL || a.epilogue == GEMV_OUT_TP_LOGITS) && (ch.tpc.tp < 2 || !ch.tpc.epoch)) return cudaErrorInvalidValue;
+    if (a.epilogue == GEMV_OUT_TP_PARTIAL && i + 1 == ch.n) return cudaErrorInvalidValue;  // the reduce lives in the next phase
     if (a.N / 2 < grid) grid = a.N / 2;
   }
   if (ch.n > 1 && (!ch.barrier || grid > num_sms)) return cudaErrorInvalidValue;

@@ -127,21 +127,22 @@ __global__ void __launch_bounds__(256) decode_embed_kernel(const __nv_bfloat16* 
     *reinterpret_cast<float4*>(dst + k + 4) = make_float4(bf16lo(v.z), bf16hi(v.z), bf16lo(v.w), bf16hi(v.w));
   }
 }
-__global__ void advance_kernel(int32_t* pos, int R, int32_t* step) {
+__global__ void advance_kernel(int32_t* pos, int R, int32_t* step, int32_t* epoch) {
   pdl_wait();
   pdl_launch_dependents();
   const int i = threadIdx.x + blockIdx.x * blockDim.x;
   if (pos && i < R) pos[i] += 1;
   if (step && i == 0) *step += 1;
+  if (epoch && i == 0) *epoch += 1;
 }
 cudaError_t launch_decode_embed(const void* table, const int64_t* tokens, float* resid, int B, int S, int H,
                                 cudaStream_t stream) {
   decode_embed_kernel<<<B * S, 256, 0, stream>>>((const __nv_bfloat16*)table, tokens, resid, B, H);
   return cudaGetLastError();
 }
-cudaError_t launch_advance(int32_t* pos, int R, int32_t* step, cudaStream_t stream) {
+cudaError_t launch_advance(int32_t* pos, int R, int32_t* step, cudaStream_t stream, int32_t* epoch) {
   const int n = R > 1 ? R : 1;
-  advance_kernel<<<(n + 127) / 128, 128, 0, stream>>>(pos, R, step);
+  advance_kernel<<<(n + 127) / 128, 128, 0, stream>>>(pos, R, step, epoch);
   return cudaGetLastError();
 }
 

@@ -131,6 +131,12 @@ struct vdd_engine {
   int graph_nodes = 0;
   // TP
   ncclComm_t comm = nullptr;
+  void* comm_buf = nullptr;        // this rank's peer-visible communication buffer (see TpComm in kernels.h)
+  size_t comm_bytes = 0;
+  TpComm tpc;                      // filled by vdd_tp_comm_open
+  bool tp_fused_ready = false;     // peers mapped: decode uses the in-kernel all-reduce instead of NCCL
+  int32_t* d_epoch = nullptr;      // decode steps since the last prefill (targets of the monotonic arrival counters)
+  float* logits_cur = nullptr;     // where the last prefill / decode step left its logits
   // stats
   int64_t launches = 0;
   float t_vision = 0, t_prefill = 0, t_decode = 0;
@@ -321,6 +327,10 @@ extern "C" void vdd_destroy(vdd_engine* e) {
   for (int i = 0; i < 4; ++i)
     if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  for (int k = 0; k < 8; ++k)
+    if (e->tp_fused_ready && k != e->c.tp_rank && e->tpc.peers[k]) cudaIpcCloseMemHandle((void*)e->tpc.peers[k]);
+  if (e->comm_buf) cudaFree(e->comm_buf);
+  if (e->d_epoch) cudaFree(e->d_epoch);
   delete e;
 }
 
@@ -656,6 +666,12 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   CK(up(e->d_head_stride, head_stride.data(), (size_t)R * 8));
   CK(cudaMemsetAsync(e->d_counters, 0, (size_t)R * e->heads_l * 4, st));
   CK(cudaMemsetAsync(e->d_step, 0, 4, st));
+  if (e->tp_fused_ready) {
+    // arrival counters and the epoch restart together; peers cannot reach a decode step (and touch these counters)
+    // before this rank has run the prefill collectives that are enqueued after this memset
+    CK(cudaMemsetAsync(e->comm_buf, 0, 4096, st));
+    CK(cudaMemsetAsync(e->d_epoch, 0, 4, st));
+  }
   CK(cudaStreamSynchronize(st));  // host vectors go out of scope
 
   // ---- layers over the concatenated rows of all streams
@@ -702,6 +718,7 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
     RC(do_gemm(e, e->xn_d, e->lm_head, R, e->Vl, H, GEMM_OUT_F32, nullptr, nullptr, lg, nullptr, e->Vl, st));
   }
   if (c.tp_size > 1) RC(tp_gather_logits(e, st));
+  e->logits_cur = (float*)e->logits.p;
   e->prefilled = true;
   return VDD_OK;
 }
@@ -742,14 +759,17 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
   const int H = c.hidden_size, L = c.num_layers, Hl = e->Hl, Il = e->Il, R = e->R;
   const bool pdl = e->use_pdl;
   const bool tp = c.tp_size > 1;
-  const bool fused = R <= 8 && !tp && e->use_fused;  // o -> gate_up -> down -> next qkv in one launch per layer
+  const bool tpf = tp && e->tp_fused_ready;             // all-reduce / all-gather inside the chain, over peer memory
+  const bool fused = R <= 8 && (!tp || tpf) && e->use_fused;  // o -> gate_up -> down -> next qkv in one launch per layer
   __nv_bfloat16* kbase = (__nv_bfloat16*)e->kv.p;
   float* lg = tp ? (float*)e->logits_tp.p : (float*)e->logits.p;
   auto qkv_args = [&](int l) {
     return gv_args(e->lw[l].wqkv, nullptr, e->resid_d, e->lw[l].ln1, c.rms_eps, R, 3 * Hl, H, GEMV_OUT_F32, e->qkv_d, nullptr, 3 * Hl);
   };
   auto head_args = [&]() {
-    return gv_args(e->lm_head, nullptr, e->resid_d, e->final_norm, c.rms_eps, R, e->Vl, H, GEMV_OUT_F32, lg, nullptr, e->Vl);
+    GemvArgs g = gv_args(e->lm_head, nullptr, e->resid_d, e->final_norm, c.rms_eps, R, e->Vl, H, GEMV_OUT_F32, lg, nullptr, e->Vl);
+    if (tpf && fused) { g.epilogue = GEMV_OUT_TP_LOGITS; g.tp_counter = 2 * L; }
+    return g;
   };
   if (fused) CK(cudaMemsetAsync(e->d_bar, 0, (size_t)(L + 2) * 4 * 4, st));
   if (!projections_only) LK(e, launch_decode_embed(e->embed, tokens, e->resid_d, e->B, e->S, H, st));
@@ -772,9 +792,15 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     if (!projections_only) LK(e, launch_decode_attn(da, st));
     if (fused) {
       GemvChain ch{};
-      ch.ph[0] = gv_args(w.wo, e->attn_d, nullptr, nullptr, 0.f, R, H, Hl, GEMV_OUT_ADD_RESID, e->resid_d, nullptr, H);
+      const int res_epi = tpf ? GEMV_OUT_TP_PARTIAL : GEMV_OUT_ADD_RESID;
+      ch.ph[0] = gv_args(w.wo, e->attn_d, nullptr, nullptr, 0.f, R, H, Hl, res_epi, e->resid_d, nullptr, H);
       ch.ph[1] = gv_args(w.wgu, nullptr, e->resid_d, w.ln2, c.rms_eps, R, 2 * Il, H, GEMV_OUT_SWIGLU_BF16, nullptr, e->h_d, Il);
-      ch.ph[2] = gv_args(w.wdown, e->h_d, nullptr, nullptr, 0.f, R, H, Il, GEMV_OUT_ADD_RESID, e->resid_d, nullptr, H);
+      ch.ph[2] = gv_args(w.wdown, e->h_d, nullptr, nullptr, 0.f, R, H, Il, res_epi, e->resid_d, nullptr, H);
+      if (tpf) {
+        ch.ph[0].tp_slot = 0; ch.ph[0].tp_counter = 2 * l;
+        ch.ph[2].tp_slot = 1; ch.ph[2].tp_counter = 2 * l + 1;
+        ch.tpc = e->tpc;
+      }
       ch.ph[3] = l + 1 < L ? qkv_args(l + 1) : head_args();
       ch.n = 4;
       ch.barrier = e->d_bar + (size_t)l * 4;
@@ -810,7 +836,8 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
       RC(do_gemm(e, e->xn_d, e->lm_head, R, e->Vl, H, GEMM_OUT_F32, nullptr, nullptr, lg, nullptr, e->Vl, st));
     }
   }
-  if (tp) RC(tp_gather_logits(e, st));
+  if (tp && !(tpf && fused)) RC(tp_gather_logits(e, st));
+  if (!projections_only) e->logits_cur = (tpf && fused) ? (float*)((char*)e->comm_buf + e->tpc.off_logits) : (float*)e->logits.p;
   return VDD_OK;
 }
 
@@ -819,10 +846,10 @@ extern "C" int vdd_decode_step(vdd_engine* e, const int64_t* tokens, void* strea
   if (!e->prefilled) return fail(VDD_ERR_STATE, "vdd_prefill must run first");
   cudaStream_t st = (cudaStream_t)stream_v;
   RC(decode_step_enqueue(e, tokens, st));
-  LK(e, launch_advance(e->d_pos, e->R, nullptr, st));  // pos += 1
+  LK(e, launch_advance(e->d_pos, e->R, nullptr, st, e->d_epoch));  // pos += 1 (and the TP epoch)
   return VDD_OK;
 }
-extern "C" float* vdd_logits(vdd_engine* e) { return e ? (float*)e->logits.p : nullptr; }
+extern "C" float* vdd_logits(vdd_engine* e) { return e ? (e->logits_cur ? e->logits_cur : (float*)e->logits.p) : nullptr; }
 extern "C" int vdd_num_streams(vdd_engine* e) { return e ? e->S : 0; }
 
 // ------------------------------------------------------------------------------------------------ K8 stand-alone
@@ -929,11 +956,23 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
     memcpy(e->pinned, &a, sizeof a);
     CK(cudaMemcpyAsync(e->d_sargs, e->pinned, sizeof a, cudaMemcpyHostToDevice, st));
   }
+  if (e->tp_fused_ready && e->R <= 8 && e->use_fused && max_new > 1) {
+    // decode steps leave their (all-gathered) logits in the peer-visible buffer: re-point the sampler there
+    CK(cudaStreamSynchronize(st));
+    float* cl = (float*)((char*)e->comm_buf + e->tpc.off_logits);
+    const bool alias = a.u == a.l;
+    a.l = cl;
+    int sj = 1;
+    a.u = alias ? cl : (a.u ? cl + (size_t)(sj++) * B * V : nullptr);
+    a.d = a.d ? cl + (size_t)(sj++) * B * V : nullptr;
+    memcpy(e->pinned, &a, sizeof a);
+    CK(cudaMemcpyAsync(e->d_sargs, e->pinned, sizeof a, cudaMemcpyHostToDevice, st));
+  }
   CK(cudaEventRecord(e->ev[2], st));
 
   int steps = 1;
   if (max_new > 1) {
-    const uint64_t key = ((uint64_t)B << 40) ^ ((uint64_t)S << 32) ^ ((uint64_t)e->max_splits << 16) ^ (uint64_t)(e->use_pdl ? 1 : 0) ^ (uint64_t)(e->use_fused ? 2 : 0) ^
+    const uint64_t key = ((uint64_t)B << 40) ^ ((uint64_t)S << 32) ^ ((uint64_t)e->max_splits << 16) ^ (uint64_t)(e->use_pdl ? 1 : 0) ^ (uint64_t)(e->use_fused ? 2 : 0) ^ (uint64_t)(e->tp_fused_ready ? 8 : 0) ^
                          (uint64_t)((a.top_p < 1.0f || (a.top_k > 1 && a.top_k < V)) ? 4 : 0) ^  // which K8 kernel the graph holds
                          ((uint64_t)(uintptr_t)e->kv.p << 1) ^ (uint64_t)(uintptr_t)e->logits.p ^ ((uint64_t)e->kv_layer_stride << 3);
     int per_step_launches = 0;
@@ -947,7 +986,7 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
       if (rc == VDD_OK) {
         cudaError_t ce = launch_combine_sample(a, e->d_sargs, B, V, st);
         e->launches++;
-        if (ce == cudaSuccess) ce = launch_advance(e->d_pos, e->R, e->d_step, st);
+        if (ce == cudaSuccess) ce = launch_advance(e->d_pos, e->R, e->d_step, st, e->d_epoch);
         e->launches++;
         if (ce != cudaSuccess) rc = fail(VDD_ERR_CUDA, "capture: %s", cudaGetErrorString(ce));
       }
@@ -969,7 +1008,7 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
       } else {
         RC(decode_step_enqueue(e, e->d_tokens, st));
         LK(e, launch_combine_sample(a, e->d_sargs, B, V, st));
-        LK(e, launch_advance(e->d_pos, e->R, e->d_step, st));
+        LK(e, launch_advance(e->d_pos, e->R, e->d_step, st, e->d_epoch));
       }
       steps = i + 1;
       // all rows finished? (vcd_sample.py:291: one host sync per step there; here every 16 steps)
@@ -1047,6 +1086,51 @@ extern "C" int vdd_tp_init(vdd_engine* e, const void* id128) {
   memcpy(nid.b, id128, 128);
   int r = g_nccl.CommInitRank(&e->comm, e->c.tp_size, nid, e->c.tp_rank);
   if (r != 0) return fail(VDD_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return VDD_OK;
+}
+
+// Peer-memory communication buffer for the in-kernel all-reduce (one per rank, exchanged as cudaIpc handles).
+extern "C" int vdd_tp_comm_handle(vdd_engine* e, void* handle64) {
+  if (!e || !handle64) return fail(VDD_ERR_ARG, "null argument");
+  if (e->c.tp_size <= 1 || e->c.tp_size > 8) return fail(VDD_ERR_UNSUPPORTED, "peer communication supports 2..8 ranks");
+  if (!e->comm_buf) {
+    const size_t inbox = (size_t)2 * e->c.tp_size * 8 * e->c.hidden_size * 4;
+    const size_t logits = (size_t)8 * e->c.vocab_size * 4;
+    e->tpc.off_inbox = 4096;
+    e->tpc.off_logits = 4096 + (long long)align_up(inbox, 256);
+    e->comm_bytes = (size_t)e->tpc.off_logits + logits;
+    CK(cudaMalloc(&e->comm_buf, e->comm_bytes));
+    CK(cudaMemset(e->comm_buf, 0, e->comm_bytes));
+    CK(cudaMalloc(&e->d_epoch, 4));
+    CK(cudaMemset(e->d_epoch, 0, 4));
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, e->comm_buf));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  memcpy(handle64, &h, 64);
+  return VDD_OK;
+}
+extern "C" int vdd_tp_comm_open(vdd_engine* e, const void* handles) {
+  if (!e || !handles || !e->comm_buf) return fail(VDD_ERR_STATE, "vdd_tp_comm_handle must run first");
+  const int tp = e->c.tp_size;
+  for (int k = 0; k < tp; ++k) {
+    if (k == e->c.tp_rank) {
+      e->tpc.peers[k] = (unsigned long long)(uintptr_t)e->comm_buf;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)k * 64, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    e->tpc.peers[k] = (unsigned long long)(uintptr_t)p;
+  }
+  e->tpc.tp = tp;
+  e->tpc.rank = e->c.tp_rank;
+  e->tpc.H = e->c.hidden_size;
+  e->tpc.V = e->c.vocab_size;
+  e->tpc.Vl = e->Vl;
+  e->tpc.epoch = e->d_epoch;
+  e->tp_fused_ready = getenv("VDD_TP_NCCL_ONLY") == nullptr;
   return VDD_OK;
 }
 

@@ -22,7 +22,14 @@ cudaError_t launch_combine_sample(const SampleArgs& args, const SampleArgs* dptr
 
 // ---------------------------------------------------------------- decode GEMV (R <= 8 rows of x against W[N,K])
 enum GemvPrologue { GEMV_X_BF16 = 0, GEMV_X_RMSNORM = 1 };
-enum GemvEpilogue { GEMV_OUT_F32 = 0, GEMV_OUT_ADD_RESID = 1, GEMV_OUT_SWIGLU_BF16 = 2 };
+enum GemvEpilogue {
+  GEMV_OUT_F32 = 0,
+  GEMV_OUT_ADD_RESID = 1,
+  GEMV_OUT_SWIGLU_BF16 = 2,
+  GEMV_OUT_TP_PARTIAL = 3,  // row-parallel projection under tensor parallelism: partial sums go to EVERY rank's inbox over NVLink;
+                            // the next phase of the chain waits for all ranks, reduces into out_f32 (the residual) and goes on
+  GEMV_OUT_TP_LOGITS = 4    // vocab-parallel lm_head: this rank's logit columns are stored into every rank's full logits
+};
 struct GemvArgs {
   const void* w;        // bf16 [N, K] row-major
   const void* x_bf16;   // bf16 [R, K] (GEMV_X_BF16)
@@ -34,14 +41,28 @@ struct GemvArgs {
   float* out_f32;       // [R, N] (OUT_F32: store; ADD_RESID: +=)
   void* out_bf16;       // [R, N/2] (SWIGLU)
   int64_t ld_out;       // row pitch of the output in elements
+  int tp_slot = 0;      // TP epilogues: inbox slot (0/1) ...
+  int tp_counter = 0;   // ... and index of the cross-GPU arrival counter
 };
 cudaError_t launch_gemv(const GemvArgs& a, int num_sms, bool pdl, cudaStream_t stream);
+// Peer-memory view of a tensor-parallel group: every rank owns one communication buffer
+//   [0, 4096)            arrival counters (u32), monotonically increasing: target = (epoch + 1) * tp * grid
+//   [off_inbox, ...)     inbox  [2 slots][tp sources][8 rows][H] fp32
+//   [off_logits, ...)    logits [8 rows][V] fp32
+// and can address all of them (cudaIpc-mapped) at peers[rank].
+struct TpComm {
+  int tp = 1, rank = 0, H = 0, V = 0, Vl = 0;
+  unsigned long long peers[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long off_inbox = 0, off_logits = 0;
+  const int32_t* epoch = nullptr;
+};
 // up to four projections in ONE launch, separated by grid barriers (barrier: n-1 counters, zero on entry)
 struct GemvChain {
   GemvArgs ph[4];
   int n;
   int ksmul = 8;  // set by the launcher
   unsigned* barrier;
+  TpComm tpc;
   unsigned long long* trace;  // debug: [grid][4 phases][8 slots] globaltimer stamps of thread 0, or null
 };
 cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaStream_t stream);
@@ -123,7 +144,7 @@ cudaError_t launch_vit_embed(const float* patch_out, const void* cls_bf16, const
                              int NP, int H, cudaStream_t stream);
 cudaError_t launch_decode_embed(const void* table_bf16, const int64_t* tokens, float* resid, int B, int S, int H,
                                 cudaStream_t stream);
-cudaError_t launch_advance(int32_t* pos, int R, int32_t* step, cudaStream_t stream);  // pos[r] += 1, *step += 1
+cudaError_t launch_advance(int32_t* pos, int R, int32_t* step, cudaStream_t stream, int32_t* epoch = nullptr);  // pos[r] += 1, *step += 1, *epoch += 1
 cudaError_t launch_add_rows(float* dst, const float* src, int64_t n, cudaStream_t stream);
 cudaError_t launch_reduce_splits(float* dst, const float* ws, int64_t n, int splits, cudaStream_t stream);  // dst += sum_z ws[z]
 cudaError_t launch_cast_rows_bf16(const float* src, void* dst_bf16, int rows, int H, const int32_t* row_idx,

@@ -142,6 +142,24 @@ class VddEngine:
         b = C.create_string_buffer(id_bytes, 128)
         _lib.check(self.lib.vdd_tp_init(self.h, b), "vdd_tp_init")
 
+    def tp_setup(self, dist):
+        """Join the tensor-parallel group through an initialised torch.distributed process group: NCCL communicator for
+        the GEMM-sized paths, cudaIpc-mapped peer buffers for the in-kernel all-reduce of the decode chain."""
+        dev = self.device
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if self.tp_rank == 0:
+            idt = torch.frombuffer(bytearray(self.tp_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(idt, 0)
+        self.tp_init(bytes(idt.cpu().numpy().tobytes()))
+        h = C.create_string_buffer(64)
+        _lib.check(self.lib.vdd_tp_comm_handle(self.h, h), "vdd_tp_comm_handle")
+        mine = torch.frombuffer(bytearray(h.raw), dtype=torch.uint8).to(dev)
+        allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(self.tp_size)]
+        dist.all_gather(allh, mine)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        _lib.check(self.lib.vdd_tp_comm_open(self.h, C.create_string_buffer(blob, len(blob))), "vdd_tp_comm_open")
+        dist.barrier()
+
     @staticmethod
     def tp_unique_id() -> bytes:
         b = C.create_string_buffer(128)

@@ -32,11 +32,7 @@ def _worker(rank, world, port, ret):
     evolve_vcd_sampling()
     m = LlavaLlamaForCausalLM(cfg, f"cuda:{rank}", tp_size=world, tp_rank=rank)
     m.load_state_dict(sd)
-    idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{rank}")
-    if rank == 0:
-        idt = torch.frombuffer(bytearray(E.VddEngine.tp_unique_id()), dtype=torch.uint8).to(f"cuda:{rank}")
-    dist.broadcast(idt, 0)
-    m.engine.tp_init(bytes(idt.cpu().numpy().tobytes()))
+    m.engine.tp_setup(dist)
     ids, img = make_inputs(cfg, 2, 12, 9)
     n = 6
     m.engine.encode_images(img)
