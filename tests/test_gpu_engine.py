@@ -136,3 +136,33 @@ def test_generate_surface(engine_model):
     c1 = m.generate(ids.cuda(), images=img.cuda(), images_cd=(img + 0.5 * torch.randn_like(img)).cuda(), cd_alpha=1.0, cd_beta=0.1,
                     do_sample=True, top_k=1, max_new_tokens=5, eos_token_id=None)
     assert c1.shape == (1, 17) and torch.equal(c1[:, :12].cpu(), ids)
+
+
+@pytest.mark.parametrize("B,use_unk,use_none,with_image,T", [(2, True, True, True, 10), (3, True, True, True, 9),
+                                                            (4, True, False, True, 7), (1, False, False, False, 5),
+                                                            (2, True, False, False, 6), (5, True, True, True, 4)])
+def test_row_shapes_against_oracle(engine_model, B, use_unk, use_none, with_image, T):
+    """Row counts on both sides of the GEMV / tensor-core decode switch (R = 6, 9, 8, 1, 4, 15), text-only prompts, and the
+    row-wise definition of the use_dd stream for B > 1, teacher-forced on the oracle's tokens."""
+    cfg, m, oracle = engine_model
+    ids, img = make_inputs(cfg, B, T, 200 + B + T)
+    if not with_image:
+        ids[ids < 0] = 7
+    n = 4
+    ref = oracle.generate(ids, img if with_image else None, use_dd=use_none, use_dd_unk=use_unk, cd_alpha=1.0, cd_beta=0.1, top_k=1,
+                          max_new_tokens=n, keep_stream_logits=True, eos_token_id=None)
+    eng = m.engine
+    if with_image:
+        eng.encode_images(img)
+    lg = eng.prefill(ids, with_image, use_unk, use_none, n)
+    names = ["m"] + (["u"] if use_unk else []) + (["d"] if use_none else [])
+    for step in range(n):
+        got = lg.cpu()
+        for si, nm in enumerate(names):
+            err = (got[si] - ref.stream_logits[step][nm]).abs().max().item()
+            assert err <= LOGIT_TOL, (step, nm, err)
+        if step + 1 < n:
+            lg = eng.decode_step(ref.sequences[:, T + step])
+    out = m.generate(ids, images=img if with_image else None, use_dd=use_none, use_dd_unk=use_unk, cd_alpha=1.0, cd_beta=0.1,
+                     do_sample=True, top_k=1, max_new_tokens=1, eos_token_id=None)
+    assert out.shape == (B, T + 1)
