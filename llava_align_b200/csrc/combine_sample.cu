@@ -254,29 +254,18 @@ __global__ void __launch_bounds__(CS_THREADS, 1) combine_sample_kernel(const Sam
   }
 
   // ---- scores (vcd_sample.py:200), softmax + multinomial (:201-202)
-  float m = -INFINITY;
 #pragma unroll
   for (int j = 0; j < CS_ITEMS; ++j) {
     const int e = j * CS_THREADS + tid;
-    if (e < V) {
-      if (scores_out) scores_out[e] = v[j];
-      m = fmaxf(m, v[j]);
-    }
+    if (scores_out && e < V) scores_out[e] = v[j];
   }
-  m = block_reduce<true>(m, redf);
-  if (q) {  // v becomes the race key p/q in place (registers are the budget at 1024 threads)
-    float z = 0.f;
-#pragma unroll
-    for (int j = 0; j < CS_ITEMS; ++j) {
-      v[j] = expf(v[j] - m);  // exp(-inf) = 0
-      z += v[j];
-    }
-    z = block_reduce<false>(z, redf);
-    const float rz = 1.0f / z;
+  if (q) {
+    // torch.multinomial(softmax(s), 1) == argmax_e softmax(s)_e / q_e == argmax_e (s_e - log q_e): the normaliser and the
+    // row maximum cancel in the ORDER, so neither the sum of exponentials nor a second row reduction is needed.
 #pragma unroll
     for (int j = 0; j < CS_ITEMS; ++j) {
       const int e = j * CS_THREADS + tid;
-      v[j] = e < V ? __fdividef(v[j] * rz, __ldg(q + e)) : -1.f;  // only the ORDER of p/q matters
+      v[j] = e < V ? v[j] - logf(__ldg(q + e)) : -INFINITY;
     }
   }
   // argmax, lowest index on ties: pack (orderable key bits, ~index) into 64 bits
@@ -384,11 +373,11 @@ combine_sample_cluster_kernel(const SampleArgs byval, const SampleArgs* dptr) {
 #pragma unroll
     for (int j = 0; j < CC_ITEMS; ++j) v[j] = __fdiv_rn(v[j], a.temperature);
   }
-  float m = -INFINITY;
+  if (a.top_k == 1) {  // TopK(1): everything below the row maximum goes (ties stay)
+    float m = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < CC_ITEMS; ++j) m = fmaxf(m, v[j]);
-  m = cluster_reduce_f(cl, m, &pub[1], redf, true);
-  if (a.top_k == 1) {  // TopK(1): everything below the maximum goes (ties stay)
+    for (int j = 0; j < CC_ITEMS; ++j) m = fmaxf(m, v[j]);
+    m = cluster_reduce_f(cl, m, &pub[1], redf, true);
 #pragma unroll
     for (int j = 0; j < CC_ITEMS; ++j)
       if (v[j] < m) v[j] = -INFINITY;
@@ -398,22 +387,11 @@ combine_sample_cluster_kernel(const SampleArgs byval, const SampleArgs* dptr) {
     const int e = e0 + j * CC_THREADS;
     if (scores_out && e < V) scores_out[e] = v[j];
   }
-  if (q) {
-    float qv[CC_ITEMS];
-    float z = 0.f;
+  if (q) {  // argmax_e softmax(s)_e / q_e == argmax_e (s_e - log q_e): no normaliser, no second row reduction
 #pragma unroll
     for (int j = 0; j < CC_ITEMS; ++j) {
       const int e = e0 + j * CC_THREADS;
-      qv[j] = e < V ? __ldg(q + e) : 1.f;
-      v[j] = expf(v[j] - m);
-      z += v[j];
-    }
-    z = cluster_reduce_f(cl, z, &pub[2], redf, false);
-    const float rz = 1.0f / z;
-#pragma unroll
-    for (int j = 0; j < CC_ITEMS; ++j) {
-      const int e = e0 + j * CC_THREADS;
-      v[j] = e < V ? __fdividef(v[j] * rz, qv[j]) : -1.f;
+      v[j] = e < V ? v[j] - logf(__ldg(q + e)) : -INFINITY;
     }
   }
   unsigned long long best = 0ull;

@@ -106,6 +106,9 @@ class LlavaLlamaForCausalLM:
             raise ValueError(f"The following `model_kwargs` are not used by the model: {sorted(kwargs)}")  # HF _validate_model_kwargs
         if num_beams != 1:
             raise NotImplementedError("beam search is outside the VDD path (reference scripts use num_beams=1)")
+        if stopping_criteria is not None and len(stopping_criteria) > 0:
+            # the reference's drivers build a KeywordsStoppingCriteria but never pass it (llava_sampling.py:91-109)
+            raise NotImplementedError("custom stopping_criteria are not supported: EOS and max_new_tokens stop generation")
         if input_ids.dim() == 1:
             input_ids = input_ids.unsqueeze(0)
         B, T = input_ids.shape
