@@ -102,6 +102,11 @@ VDD_API int vdd_prefill(vdd_engine* e, const int64_t* ids_host, int B, int T, in
 /* Prefill of the main stream plus the VCD contrast stream (same prompt, images_cd features spliced in): step 0 of
  * reference vcd_sample.py:148-150,161-169.  Streams: main, cd. */
 VDD_API int vdd_prefill_cd(vdd_engine* e, const int64_t* ids_host, int B, int T, int max_new_tokens, void* stream);
+/* Arms the NEXT prefill (vdd_prefill / vdd_generate*) to also write the step-0 attention map of the LAST layer of the main
+ * stream -- the `attentions[0][-1]` of generate(output_attentions=True) that the reference's post-hoc-debias drivers read
+ * (llava_calibrate.py:180-182, vcd_sample.py:241-246) -- into out: fp32 [B, heads, len, len], len = prompt length after
+ * the image splice, zeros above the diagonal.  elems must equal B*heads*len*len.  out = NULL disarms.  Not under TP. */
+VDD_API int vdd_set_attention_capture(vdd_engine* e, float* out, int64_t elems);
 /* One decode step for all S*B rows: row (s,b) consumes tokens[b].  Leaves logits in vdd_logits(). */
 VDD_API int vdd_decode_step(vdd_engine* e, const int64_t* tokens, void* stream);
 VDD_API float* vdd_logits(vdd_engine* e); /* fp32 [S, B, V] */
@@ -118,7 +123,9 @@ VDD_API int vdd_generate(vdd_engine* e, const int64_t* ids_host, int B, int T, c
 
 /* Same with the VCD contrast stream: pixels_cd_host bf16 [B,3,S,S] (NULL => identical to vdd_generate).  As in the
  * reference (vcd_sample.py:148-150) only step 0 contrasts against the noised image; from step 1
- * the contrast logits are the main logits.  Excludes use_unk / use_none. */
+ * the contrast logits are the main logits.  With use_unk / use_none the reference's precedence applies
+ * (vcd_sample.py:148,171-185): the cd forward replaces the unk stream, and the 'none' stream joins (cd = (cd + none)/2)
+ * only when BOTH flags are set. */
 VDD_API int vdd_generate_cd(vdd_engine* e, const int64_t* ids_host, int B, int T, const void* pixels_host,
                     const void* pixels_cd_host, int use_unk, int use_none, const vdd_sample_params* params_host,
                     int max_new_tokens, const float* q_exp, float* scores_out, int64_t* tokens_out_host, int* steps_out,
@@ -147,6 +154,15 @@ VDD_API int vdd_gemv(const void* w_bf16, const void* x_bf16, const float* x_f32_
              int R, int N, int K, int epilogue, float* out_f32, void* out_bf16, void* stream);
 VDD_API int vdd_gemm(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue, const void* bias_bf16,
              const int32_t* row_map, float* out_f32, void* out_bf16, int64_t ldc, void* stream);
+
+/* Decode projection for 8 < R <= 256 fused rows (stream-K tcgen05 kernel, weights as the UMMA A operand):
+ * out[r, n] = sum_k x[r, k] * w[n, k]; epilogue 0 = store fp32, 1 = += fp32, 5 = SwiGLU over interleaved gate/up -> bf16 [R, N/2]. */
+VDD_API int vdd_skinny_gemm(const void* w_bf16, const void* x_bf16, int R, int N, int K, int epilogue, float* out_f32,
+                    void* out_bf16, int64_t ld, void* stream);
+/* Debug: per-CTA %globaltimer stamps of the next vdd_skinny_gemm launches into dev_buf [148][8] u64 (NULL disarms):
+ * 0 entry, 1 first weights requested, 2 previous kernel complete, 3 first stage landed, 4 last MMA issued,
+ * 5 all segments drained, 6 last shared tile complete, 7 exit. */
+VDD_API int vdd_skinny_gemm_trace(unsigned long long* dev_buf);
 
 #ifdef __cplusplus
 }

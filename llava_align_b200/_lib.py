@@ -47,6 +47,7 @@ SIGNATURES = {
     "vdd_encode_images_cd": (C.c_int, [_P, _P, C.c_int, _P]),
     "vdd_prefill_cd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vdd_prefill": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vdd_set_attention_capture": (C.c_int, [_P, _P, C.c_int64]),
     "vdd_decode_step": (C.c_int, [_P, _P, _P]),
     "vdd_logits": (_P, [_P]),
     "vdd_num_streams": (C.c_int, [_P]),
@@ -63,6 +64,8 @@ SIGNATURES = {
     "vdd_bench_projection_chain": (C.c_int, [_P, _P]),
     "vdd_debug_trace": (C.c_int, [_P, _P, C.c_int]),
     "vdd_gemv": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "vdd_skinny_gemm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64, _P]),
+    "vdd_skinny_gemm_trace": (C.c_int, [_P]),
     "vdd_gemm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int64, _P]),
 }
 

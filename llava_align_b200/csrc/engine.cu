@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -97,7 +98,9 @@ struct vdd_engine {
   vdd_config c;
   int D = 128, heads_l = 0, Hl = 0, Il = 0, Vl = 0, NP = 0, Kpad = 0, VD = 64;
   int num_sms = 148;
-  bool use_pdl = true, use_graph = true, use_fused = true;
+  bool use_pdl = true, use_graph = true, use_fused = true, use_skinny = true;
+  int* sk_counters = nullptr;  // per decode step: one zeroed counter block per skinny GEMM launch
+  int sk_launch = 0;
   // weights
   void* arena = nullptr;
   size_t arena_bytes = 0;
@@ -109,9 +112,15 @@ struct vdd_engine {
   void *patch_w, *cls, *vpos, *preln_w, *preln_b, *pj_w1, *pj_b1, *pj_w2, *pj_b2;
   float *rope_cos = nullptr, *rope_sin = nullptr;
   // workspaces
-  DevBuf resid, xn, qkv, qb, attn, hbuf, meta, kv, logits, logits_tp, dec_f32, dec_bf16, part, img_feats, vis, pix, misc, tp_tmp, split_ws;
+  DevBuf resid, xn, qkv, qb, attn, hbuf, meta, kv, logits, logits_tp, dec_f32, dec_bf16, part, img_feats, vis, pix, misc, tp_tmp, split_ws, sk_ws, sk_cnt;
   // per-generation plan
   int B = 0, T = 0, S = 0, R = 0, Mtot = 0, max_new = 0, max_len = 0, max_splits = 1;
+  int attn_items = 0, attn_chunk = 0;  // streaming decode attention (R > 8): (row, split) work table
+  int32_t *d_item_row = nullptr, *d_item_split = nullptr;
+  float* attn_capture = nullptr;  // armed by vdd_set_attention_capture: the next prefill writes the last layer's step-0 map here
+  int64_t attn_capture_elems = 0;
+  int main_len = 0;  // length of the main-stream rows after the image splice (0: rows differ)
+  std::vector<int32_t> h_item_row;
   int64_t kv_layer_stride = 0;
   int32_t *d_tok = nullptr, *d_img_row = nullptr, *d_row_seq = nullptr, *d_row_pos = nullptr, *d_kv_cap = nullptr,
           *d_pos = nullptr, *d_last_rows = nullptr, *d_seqlen = nullptr, *d_q_row0 = nullptr, *d_step = nullptr,
@@ -202,6 +211,9 @@ extern "C" int vdd_create(const vdd_config* cfg, vdd_engine** out) {
   cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev);
   e->use_pdl = getenv("VDD_NO_PDL") == nullptr;
   e->use_graph = getenv("VDD_NO_GRAPH") == nullptr;
+  // Stand-alone stream-K launches lose to the square-tile GEMM + split-K at R = 96 (per-launch set-up, first fill, drain and
+  // the shared-tile fix-up cost ~14 us against a 15 us stream: profiles/r1_trace_skinny.json); opt-in until chained.
+  e->use_skinny = getenv("VDD_SKINNY") != nullptr;
   e->use_fused = getenv("VDD_NO_FUSED") == nullptr;
   if (getenv("VDD_TRACE")) cudaMalloc(&e->d_trace, (size_t)256 * 4 * 8 * 8);
 
@@ -317,7 +329,7 @@ extern "C" void vdd_destroy(vdd_engine* e) {
   cudaDeviceSynchronize();
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   DevBuf* bufs[] = {&e->resid, &e->xn, &e->qkv, &e->qb, &e->attn, &e->hbuf, &e->meta, &e->kv, &e->logits, &e->logits_tp,
-                    &e->dec_f32, &e->dec_bf16, &e->part, &e->img_feats, &e->vis, &e->pix, &e->misc, &e->tp_tmp, &e->split_ws};
+                    &e->dec_f32, &e->dec_bf16, &e->part, &e->img_feats, &e->vis, &e->pix, &e->misc, &e->tp_tmp, &e->split_ws, &e->sk_ws, &e->sk_cnt};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (e->arena) cudaFree(e->arena);
@@ -434,6 +446,17 @@ static int do_gemm(vdd_engine* e, const void* a, const void* w, int M, int N, in
   e->launches++;
   if (ce != cudaSuccess)
     return fail(VDD_ERR_CUDA, "gemm M=%d N=%d K=%d: %s %s", M, N, K, cudaGetErrorString(ce), gemm_init_error() ? gemm_init_error() : "");
+  return VDD_OK;
+}
+constexpr int SK_CNT_STRIDE = 256;  // counters per skinny GEMM launch (>= N/256 tiles of any projection)
+static int do_skinny(vdd_engine* e, const void* x, const void* w, int R, int N, int K, int mode, float* of32, void* obf16, int64_t ld,
+                     cudaStream_t st) {
+  if (skinny_gemm_tiles(N) > SK_CNT_STRIDE) return fail(VDD_ERR_UNSUPPORTED, "skinny gemm: N=%d too wide", N);
+  SkinnyArgs a{w, x, R, N, K, mode, of32, obf16, ld, (float*)e->sk_ws.p, e->sk_ws.bytes, e->sk_counters + (size_t)e->sk_launch * SK_CNT_STRIDE};
+  e->sk_launch++;
+  cudaError_t ce = launch_skinny_gemm(a, e->num_sms, e->use_pdl, st);
+  e->launches++;
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm R=%d N=%d K=%d: %s", R, N, K, cudaGetErrorString(ce));
   return VDD_OK;
 }
 #define RC(x)               \
@@ -559,9 +582,9 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   // ---- row plan (vcd_sample.py:152-160: unk = sentinel -> token 0; none = sentinel deleted; main = 576 image rows)
   std::vector<int> kinds;  // 0 main, 1 unk, 2 none, 3 cd (main prompt with the noised image's features)
   kinds.push_back(0);
-  if (use_cd) kinds.push_back(3);
   if (use_unk) kinds.push_back(1);
   if (use_none) kinds.push_back(2);
+  if (use_cd) kinds.push_back(3);  // last: its rows are dropped after step 0 (vdd_generate_cd)
   std::vector<int32_t> tok, img_row, row_seq, row_pos, seqlen(R), q_row0(R), kv_cap(R), last_rows(R);
   std::vector<int64_t> kv_off(R), head_stride(R);
   int64_t kv_total = 0;
@@ -604,7 +627,25 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   const int Mtot = (int)tok.size();
   e->B = B; e->T = T; e->S = S; e->R = R; e->Mtot = Mtot; e->max_new = max_new; e->max_len = max_len;
   e->kv_layer_stride = kv_total;
+  e->main_len = seqlen[0];
+  for (int b = 1; b < B; ++b)
+    if (seqlen[b] != seqlen[0]) e->main_len = 0;
   e->max_splits = (max_len + max_new + 63) / 64;
+  // streaming decode attention for many rows: each row gets the splits its capacity can ever need, long rows first
+  std::vector<int32_t> item_row, item_split;
+  e->attn_items = 0;
+  e->attn_chunk = 0;
+  if (R > 8 && !getenv("VDD_ATTN_LEGACY")) {
+    // measured on B200 (config 3, 96 rows, ms per decode step): 64-token kernel 8.51; chunk 128: 9.14, 512: 7.85, 1024: 7.40 --
+    // one CTA per (row, head) up to 1024 tokens beats finer splits + merges even though main rows are 7x the debias rows
+    int chunk = getenv("VDD_ATTN_CHUNK") ? atoi(getenv("VDD_ATTN_CHUNK")) : 1024;
+    if (chunk < 64 || chunk % 64) chunk = 1024;
+    for (int q = 0; q < R; ++q)
+      for (int sp = 0; sp * chunk < kv_cap[q]; ++sp) { item_row.push_back(q); item_split.push_back(sp); }
+    e->attn_items = (int)item_row.size();
+    e->attn_chunk = chunk;
+  }
+  e->h_item_row = item_row;
 
   // ---- buffers
   RC(ensure(e, e->resid, (size_t)Mtot * H * 4));
@@ -616,6 +657,14 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   RC(ensure(e, e->kv, (size_t)2 * L * kv_total * 2));
   RC(ensure(e, e->logits, (size_t)R * c.vocab_size * 4));
   if (R > 8 && R <= 128) RC(ensure(e, e->split_ws, (size_t)8 * R * H * 4));
+  if (R > 8 && R <= 256 && e->use_skinny) {
+    size_t ws = 0;
+    const int shapes[5][2] = {{3 * Hl, H}, {H, Hl}, {2 * Il, H}, {H, Il}, {e->Vl, H}};
+    for (auto& sh : shapes) ws = std::max(ws, skinny_gemm_ws_bytes(R, sh[0], sh[1], e->num_sms));
+    RC(ensure(e, e->sk_ws, ws));
+    RC(ensure(e, e->sk_cnt, (size_t)(4 * L + 1) * SK_CNT_STRIDE * 4));
+    e->sk_counters = (int*)e->sk_cnt.p;
+  }
   if (c.tp_size > 1) {
     RC(ensure(e, e->logits_tp, (size_t)R * c.vocab_size * 4));
     RC(ensure(e, e->tp_tmp, (size_t)(Mtot > R ? Mtot : R) * H * 4));
@@ -642,7 +691,8 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
                  o_cap = carve((size_t)R * 4), o_pos = carve((size_t)R * 4), o_last = carve((size_t)R * 4), o_len = carve((size_t)R * 4),
                  o_q0 = carve((size_t)R * 4), o_step = carve(256), o_unf = carve((size_t)B * 4), o_cnt = carve((size_t)R * e->heads_l * 4),
                  o_off = carve((size_t)R * 8), o_hs = carve((size_t)R * 8), o_tokens = carve((size_t)B * 8),
-                 o_seq = carve((size_t)B * max_new * 8), o_sa = carve(sizeof(SampleArgs)), o_bar = carve((size_t)(L + 2) * 4 * 4);
+                 o_seq = carve((size_t)B * max_new * 8), o_sa = carve(sizeof(SampleArgs)), o_bar = carve((size_t)(L + 2) * 4 * 4),
+                 o_ir = carve((size_t)(e->attn_items + 1) * 4), o_is = carve((size_t)(e->attn_items + 1) * 4);
     RC(ensure(e, e->meta, o));
     char* b = (char*)e->meta.p;
     e->d_tok = (int32_t*)(b + o_tok); e->d_img_row = (int32_t*)(b + o_img); e->d_row_seq = (int32_t*)(b + o_rs);
@@ -651,6 +701,7 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
     e->d_step = (int32_t*)(b + o_step); e->d_unfinished = (int32_t*)(b + o_unf); e->d_counters = (int32_t*)(b + o_cnt);
     e->d_kv_off = (int64_t*)(b + o_off); e->d_head_stride = (int64_t*)(b + o_hs); e->d_tokens = (int64_t*)(b + o_tokens);
     e->d_seq_out = (int64_t*)(b + o_seq); e->d_sargs = (SampleArgs*)(b + o_sa); e->d_bar = (unsigned*)(b + o_bar);
+    e->d_item_row = (int32_t*)(b + o_ir); e->d_item_split = (int32_t*)(b + o_is);
   }
   auto up = [&](void* d, const void* h, size_t n) { return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st); };
   CK(up(e->d_tok, tok.data(), (size_t)Mtot * 4));
@@ -664,6 +715,10 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   CK(up(e->d_q_row0, q_row0.data(), (size_t)R * 4));
   CK(up(e->d_kv_off, kv_off.data(), (size_t)R * 8));
   CK(up(e->d_head_stride, head_stride.data(), (size_t)R * 8));
+  if (e->attn_items) {
+    CK(up(e->d_item_row, item_row.data(), (size_t)e->attn_items * 4));
+    CK(up(e->d_item_split, item_split.data(), (size_t)e->attn_items * 4));
+  }
   CK(cudaMemsetAsync(e->d_counters, 0, (size_t)R * e->heads_l * 4, st));
   CK(cudaMemsetAsync(e->d_step, 0, 4, st));
   if (e->tp_fused_ready) {
@@ -720,6 +775,20 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   if (c.tp_size > 1) RC(tp_gather_logits(e, st));
   e->logits_cur = (float*)e->logits.p;
   e->prefilled = true;
+  if (e->attn_capture) {
+    // the roped queries of the LAST layer are still in qb and its keys are in the cache: materialise the main stream's map
+    float* out = e->attn_capture;
+    e->attn_capture = nullptr;
+    if (c.tp_size > 1) return fail(VDD_ERR_UNSUPPORTED, "attention maps are not gathered across tensor-parallel ranks");
+    if (!e->main_len) return fail(VDD_ERR_UNSUPPORTED, "attention maps need main-stream rows of equal length");
+    const int64_t need = (int64_t)B * e->heads_l * e->main_len * e->main_len;
+    if (need != e->attn_capture_elems)
+      return fail(VDD_ERR_ARG, "attention capture buffer holds %lld floats, the map needs %lld", (long long)e->attn_capture_elems, (long long)need);
+    AttnProbsArgs ap{};
+    ap.q = e->qb.p; ap.q_ld = Hl; ap.k = kbase + (size_t)(L - 1) * kv_total; ap.k_off = e->d_kv_off; ap.kv_cap = e->d_kv_cap;
+    ap.q_row0 = e->d_q_row0; ap.out = out; ap.B = B; ap.heads = e->heads_l; ap.len = e->main_len; ap.scale = 0.08838834764831845f;
+    LK(e, launch_attn_probs(ap, st));
+  }
   return VDD_OK;
 }
 
@@ -772,6 +841,15 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     return g;
   };
   if (fused) CK(cudaMemsetAsync(e->d_bar, 0, (size_t)(L + 2) * 4 * 4, st));
+  const bool skinny = R > 8 && R <= 256 && e->use_skinny && e->sk_counters;  // stream-K tcgen05 kernel instead of the square-tile GEMM
+  if (skinny) {
+    e->sk_launch = 0;
+    CK(cudaMemsetAsync(e->sk_counters, 0, (size_t)(4 * L + 1) * SK_CNT_STRIDE * 4, st));
+  }
+  auto gemm = [&](const void* x, const void* w, int N, int K, int mode, float* of32, void* obf16, int64_t ld) -> int {
+    if (skinny) return do_skinny(e, x, w, R, N, K, mode, of32, obf16, ld, st);
+    return do_gemm(e, x, w, R, N, K, mode, nullptr, nullptr, of32, obf16, ld, st);
+  };
   if (!projections_only) LK(e, launch_decode_embed(e->embed, tokens, e->resid_d, e->B, e->S, H, st));
   if (fused) LK(e, launch_gemv(qkv_args(0), e->num_sms, pdl, st));
   for (int l = 0; l < L; ++l) {
@@ -781,7 +859,7 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
         LK(e, launch_gemv(qkv_args(l), e->num_sms, pdl, st));
       } else {
         LK(e, launch_rmsnorm_bf16(e->resid_d, w.ln1, c.rms_eps, e->xn_d, R, H, nullptr, st));
-        RC(do_gemm(e, e->xn_d, w.wqkv, R, 3 * Hl, H, GEMM_OUT_F32, nullptr, nullptr, e->qkv_d, nullptr, 3 * Hl, st));
+        RC(gemm(e->xn_d, w.wqkv, 3 * Hl, H, GEMM_OUT_F32, e->qkv_d, nullptr, 3 * Hl));
       }
     }
     DecodeAttnArgs da{};
@@ -789,6 +867,7 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     da.kv_off = e->d_kv_off; da.kv_cap = e->d_kv_cap; da.pos = e->d_pos; da.rope_cos = e->rope_cos; da.rope_sin = e->rope_sin;
     da.out_bf16 = e->attn_d; da.part_o = e->part_o; da.part_ml = e->part_ml; da.counters = e->d_counters;
     da.R = R; da.heads = e->heads_l; da.max_splits = e->max_splits; da.scale = 0.08838834764831845f;
+    if (e->attn_items) { da.item_row = e->d_item_row; da.item_split = e->d_item_split; da.n_items = e->attn_items; da.chunk = e->attn_chunk; }
     if (!projections_only) LK(e, launch_decode_attn(da, st));
     if (fused) {
       GemvChain ch{};
@@ -814,7 +893,7 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     if (R <= 8) {
       LK(e, launch_gemv(gv_args(w.wo, e->attn_d, nullptr, nullptr, 0.f, R, H, Hl, o_mode_v, o_dst, nullptr, H), e->num_sms, pdl, st));
     } else {
-      RC(do_gemm(e, e->attn_d, w.wo, R, H, Hl, o_mode_m, nullptr, nullptr, o_dst, nullptr, H, st));
+      RC(gemm(e->attn_d, w.wo, H, Hl, o_mode_m, o_dst, nullptr, H));
     }
     if (tp) RC(tp_allreduce_add(e, o_dst, e->resid_d, (int64_t)R * H, st));
     if (R <= 8) {
@@ -823,8 +902,8 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
       LK(e, launch_gemv(gv_args(w.wdown, e->h_d, nullptr, nullptr, 0.f, R, H, Il, o_mode_v, o_dst, nullptr, H), e->num_sms, pdl, st));
     } else {
       LK(e, launch_rmsnorm_bf16(e->resid_d, w.ln2, c.rms_eps, e->xn_d, R, H, nullptr, st));
-      RC(do_gemm(e, e->xn_d, w.wgu, R, 2 * Il, H, GEMM_OUT_SWIGLU, nullptr, nullptr, nullptr, e->h_d, Il, st));
-      RC(do_gemm(e, e->h_d, w.wdown, R, H, Il, o_mode_m, nullptr, nullptr, o_dst, nullptr, H, st));
+      RC(gemm(e->xn_d, w.wgu, 2 * Il, H, GEMM_OUT_SWIGLU, nullptr, e->h_d, Il));
+      RC(gemm(e->h_d, w.wdown, H, Il, o_mode_m, o_dst, nullptr, H));
     }
     if (tp) RC(tp_allreduce_add(e, o_dst, e->resid_d, (int64_t)R * H, st));
   }
@@ -833,7 +912,7 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
       LK(e, launch_gemv(head_args(), e->num_sms, pdl, st));
     } else {
       LK(e, launch_rmsnorm_bf16(e->resid_d, e->final_norm, c.rms_eps, e->xn_d, R, H, nullptr, st));
-      RC(do_gemm(e, e->xn_d, e->lm_head, R, e->Vl, H, GEMM_OUT_F32, nullptr, nullptr, lg, nullptr, e->Vl, st));
+      RC(gemm(e->xn_d, e->lm_head, e->Vl, H, GEMM_OUT_F32, lg, nullptr, e->Vl));
     }
   }
   if (tp && !(tpf && fused)) RC(tp_gather_logits(e, st));
@@ -847,6 +926,12 @@ extern "C" int vdd_decode_step(vdd_engine* e, const int64_t* tokens, void* strea
   cudaStream_t st = (cudaStream_t)stream_v;
   RC(decode_step_enqueue(e, tokens, st));
   LK(e, launch_advance(e->d_pos, e->R, nullptr, st, e->d_epoch));  // pos += 1 (and the TP epoch)
+  return VDD_OK;
+}
+extern "C" int vdd_set_attention_capture(vdd_engine* e, float* out, int64_t elems) {
+  if (!e) return fail(VDD_ERR_ARG, "null engine");
+  e->attn_capture = out;
+  e->attn_capture_elems = out ? elems : 0;
   return VDD_OK;
 }
 extern "C" float* vdd_logits(vdd_engine* e) { return e ? (e->logits_cur ? e->logits_cur : (float*)e->logits.p) : nullptr; }
@@ -910,8 +995,13 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
   const vdd_config& c = e->c;
   CK(cudaEventRecord(e->ev[0], st));
   const bool use_cd = pixels_cd_host != nullptr;
-  if (use_cd && (!pixels_host || use_unk || use_none))
-    return fail(VDD_ERR_UNSUPPORTED, "images_cd needs images and excludes use_dd / use_dd_unk in this build");
+  if (use_cd && !pixels_host) return fail(VDD_ERR_ARG, "images_cd needs images");
+  if (use_cd) {
+    // reference vcd_sample.py:148: `if use_cd:` wins the first contrast forward, so the unk stream never runs; the 'none'
+    // stream is added by :171-185 only when BOTH use_dd and use_dd_unk are set
+    use_none = (use_unk && use_none) ? 1 : 0;
+    use_unk = 0;
+  }
   if (pixels_host) {
     e->image_cd_B = 0;
     RC(upload_and_encode(e, pixels_host, B, 0, st));
@@ -925,9 +1015,10 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
   SampleArgs a{};
   float* lg = (float*)e->logits.p;
   a.l = lg;
-  int si = 1;
-  a.u = (use_unk || use_cd) ? lg + (size_t)(si++) * B * V : nullptr;
+  int si = 1;  // stream order: main, unk, none, cd
+  a.u = use_unk ? lg + (size_t)(si++) * B * V : nullptr;
   a.d = use_none ? lg + (size_t)(si++) * B * V : nullptr;
+  if (use_cd) a.u = lg + (size_t)(si++) * B * V;
   a.q = q_exp; a.scores_out = scores_out; a.tokens_out = e->d_tokens; a.seq_out = e->d_seq_out; a.seq_ld = max_new;
   a.unfinished = e->d_unfinished; a.step_ptr = e->d_step; a.ld = V; a.B = B; a.V = V;
   fill_sample_args(a, *p);
@@ -949,9 +1040,14 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
     // step 1 on the "contrast" forward runs on the main KV cache and its logits equal the main logits (SURVEY Appendix A
     // Q7).  The cd rows are therefore dropped after step 0 and the combine reads l as its own contrast.
     CK(cudaStreamSynchronize(st));
-    e->S = 1;
-    e->R = B;
-    S = 1;
+    e->S = S - 1;
+    e->R = e->S * B;
+    S = e->S;
+    if (e->attn_items) {  // the work table is ordered by row: keep the surviving rows' items
+      int n = 0;
+      while (n < (int)e->h_item_row.size() && e->h_item_row[n] < e->R) ++n;
+      e->attn_items = n;
+    }
     a.u = a.l;
     memcpy(e->pinned, &a, sizeof a);
     CK(cudaMemcpyAsync(e->d_sargs, e->pinned, sizeof a, cudaMemcpyHostToDevice, st));
@@ -972,9 +1068,16 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
 
   int steps = 1;
   if (max_new > 1) {
-    const uint64_t key = ((uint64_t)B << 40) ^ ((uint64_t)S << 32) ^ ((uint64_t)e->max_splits << 16) ^ (uint64_t)(e->use_pdl ? 1 : 0) ^ (uint64_t)(e->use_fused ? 2 : 0) ^ (uint64_t)(e->tp_fused_ready ? 8 : 0) ^
-                         (uint64_t)((a.top_p < 1.0f || (a.top_k > 1 && a.top_k < V)) ? 4 : 0) ^  // which K8 kernel the graph holds
-                         ((uint64_t)(uintptr_t)e->kv.p << 1) ^ (uint64_t)(uintptr_t)e->logits.p ^ ((uint64_t)e->kv_layer_stride << 3);
+    // everything the captured nodes bake in: shapes, kernel choices and the buffers their arguments point into
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+    mix((uint64_t)B); mix((uint64_t)S); mix((uint64_t)e->R); mix((uint64_t)e->Mtot); mix((uint64_t)e->max_splits);
+    mix((uint64_t)e->attn_items); mix((uint64_t)e->attn_chunk);
+    mix((uint64_t)(e->use_pdl ? 1 : 0) | (uint64_t)(e->use_fused ? 2 : 0) | (uint64_t)(e->tp_fused_ready ? 8 : 0) | (uint64_t)(e->use_skinny ? 16 : 0) |
+        (uint64_t)((a.top_p < 1.0f || (a.top_k > 1 && a.top_k < V)) ? 4 : 0));  // bit 2: which K8 kernel the graph holds
+    mix((uint64_t)(uintptr_t)e->kv.p); mix((uint64_t)(uintptr_t)e->logits.p); mix((uint64_t)e->kv_layer_stride);
+    mix((uint64_t)(uintptr_t)e->meta.p); mix((uint64_t)(uintptr_t)e->dec_f32.p); mix((uint64_t)(uintptr_t)e->dec_bf16.p);
+    mix((uint64_t)(uintptr_t)e->sk_ws.p); mix((uint64_t)(uintptr_t)e->split_ws.p);
     int per_step_launches = 0;
     const bool graph = e->use_graph && st != nullptr;  // the legacy default stream cannot be captured
     if (graph && (!e->graph_exec || e->graph_key != key)) {
@@ -1146,6 +1249,37 @@ extern "C" int vdd_gemv(const void* w, const void* x_bf16, const float* x_resid,
   g.ld_out = epilogue == GEMV_OUT_SWIGLU_BF16 ? N / 2 : N;
   cudaError_t ce = launch_gemv(g, sms, getenv("VDD_NO_PDL") == nullptr, (cudaStream_t)stream_v);
   if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "gemv R=%d N=%d K=%d: %s", R, N, K, cudaGetErrorString(ce));
+  return VDD_OK;
+}
+static unsigned long long* g_sk_trace = nullptr;
+extern "C" int vdd_skinny_gemm(const void* w, const void* x_bf16, int R, int N, int K, int epilogue, float* out_f32, void* out_bf16,
+                               int64_t ld, void* stream_v) {
+  static float* ws = nullptr;
+  static size_t ws_bytes = 0;
+  static int* cnt = nullptr;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t need = skinny_gemm_ws_bytes(R, N, K, sms);
+  if (need > ws_bytes) {
+    if (ws) cudaFree(ws);
+    ws_bytes = 0;
+    if (cudaMalloc(&ws, need) != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm scratch: out of memory");
+    ws_bytes = need;
+  }
+  if (!cnt && cudaMalloc(&cnt, 4096 * 4) != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm counters: out of memory");
+  if (skinny_gemm_tiles(N) > 4096) return fail(VDD_ERR_UNSUPPORTED, "N too wide");
+  cudaStream_t st = (cudaStream_t)stream_v;
+  cudaMemsetAsync(cnt, 0, 4096 * 4, st);
+  SkinnyArgs a{w, x_bf16, R, N, K, epilogue, out_f32, out_bf16, ld, ws, ws_bytes, cnt};
+  a.trace = g_sk_trace;
+  cudaError_t ce = launch_skinny_gemm(a, sms, getenv("VDD_NO_PDL") == nullptr, st);
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm R=%d N=%d K=%d: %s", R, N, K, cudaGetErrorString(ce));
+  return VDD_OK;
+}
+/* Debug: arm (device buffer of [grid][8] u64 globaltimer stamps) or disarm (NULL) tracing of vdd_skinny_gemm launches. */
+extern "C" int vdd_skinny_gemm_trace(unsigned long long* dev_buf) {
+  g_sk_trace = dev_buf;
   return VDD_OK;
 }
 extern "C" int vdd_gemm(const void* a, const void* w, int M, int N, int K, int epilogue, const void* bias, const int32_t* row_map,

@@ -92,6 +92,24 @@ struct GemmArgs {
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
 const char* gemm_init_error();
 
+// ---------------------------------------------------------------- tcgen05 skinny GEMM for decode (8 < R <= 256 rows)
+// out[r, n] (op)= sum_k x[r, k] * w[n, k]; epilogue = GEMM_OUT_F32 | GEMM_OUT_ADD_F32 | GEMM_OUT_SWIGLU.
+struct SkinnyArgs {
+  const void* w;  // bf16 [N, K]
+  const void* x;  // bf16 [R, K]
+  int R, N, K, epilogue;
+  float* out_f32;
+  void* out_bf16;
+  int64_t ld;
+  float* ws;        // fp32 scratch for tiles shared by several CTAs (skinny_gemm_ws_bytes)
+  size_t ws_bytes;
+  int* counters;    // [skinny_gemm_tiles(N)] zero on entry (left non-zero)
+  unsigned long long* trace = nullptr;  // debug: [grid][8] globaltimer stamps
+};
+cudaError_t launch_skinny_gemm(const SkinnyArgs& a, int num_sms, bool pdl, cudaStream_t stream);
+size_t skinny_gemm_ws_bytes(int R, int N, int K, int num_sms);
+int skinny_gemm_tiles(int N);
+
 // ---------------------------------------------------------------- attention
 struct DecodeAttnArgs {
   const float* qkv;     // fp32 [R, 3*Hl] (q | k | v) of the new token, pre-RoPE
@@ -108,6 +126,10 @@ struct DecodeAttnArgs {
   int32_t* counters;    // [R*heads] zero on entry, zero on exit
   int R, heads, max_splits;
   float scale;
+  // streaming variant (many rows): work table of (row, split) items with `chunk` tokens per split; null => 64-token kernel
+  const int32_t* item_row = nullptr;
+  const int32_t* item_split = nullptr;
+  int n_items = 0, chunk = 0;
 };
 cudaError_t launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t stream);
 
@@ -127,6 +149,20 @@ struct PrefillAttnArgs {
   float scale;
 };
 cudaError_t launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t stream);
+
+// step-0 attention map of one layer for the first B sequences (all of length len): out [B, heads, len, len] fp32
+struct AttnProbsArgs {
+  const void* q;   // bf16 roped queries, query i of sequence b at q + (q_row0[b] + i)*q_ld + h*128
+  int64_t q_ld;
+  const void* k;   // bf16 K cache of the layer: key t of (b, h) at k + k_off[b] + h*kv_cap[b]*128 + t*128
+  const int64_t* k_off;
+  const int32_t* kv_cap;
+  const int32_t* q_row0;
+  float* out;
+  int B, heads, len;
+  float scale;
+};
+cudaError_t launch_attn_probs(const AttnProbsArgs& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------- element-wise / glue
 cudaError_t launch_rmsnorm_bf16(const float* x, const void* w_bf16, float eps, void* out_bf16, int rows, int H,

@@ -184,4 +184,60 @@ cudaError_t launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t stream) {
   return cudaErrorInvalidValue;
 }
 
+// ------------------------------------------------------------------------------------------------ attention maps
+// The `attentions[0][-1]` the reference's post-hoc-debias drivers read from generate(output_attentions=True)
+// (llava_calibrate.py:180-182, vcd_sample.py:241-246): the LAST layer's softmax(q k^T / sqrt(d)) of the main stream at
+// step 0, [B, heads, len, len] fp32 with zeros above the diagonal (HF eager attention returns the post-softmax weights).
+// Computed after the prefill from what it leaves behind -- the roped bf16 queries of the last layer and that layer's K
+// cache -- so the fused prefill attention itself never materialises a len x len matrix.  One CTA per (query, head, seq).
+constexpr int AP_THREADS = 128;
+__global__ void __launch_bounds__(AP_THREADS) attn_probs_kernel(const AttnProbsArgs a) {
+  extern __shared__ float ap_sc[];  // [len] scores of this query
+  __shared__ float q_s[128];
+  __shared__ float red[33];
+  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x;
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(a.q) + (size_t)(a.q_row0[b] + i) * a.q_ld + h * 128;
+  const __nv_bfloat16* K = reinterpret_cast<const __nv_bfloat16*>(a.k) + a.k_off[b] + (size_t)h * a.kv_cap[b] * 128;
+  q_s[tid] = __bfloat162float(q[tid]);
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = tid; j <= i; j += AP_THREADS) {
+    const uint4* kr = reinterpret_cast<const uint4*>(K + (size_t)j * 128);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const uint4 w = kr[c];
+      const float* qq = q_s + c * 8;
+      s += bf16lo(w.x) * qq[0] + bf16hi(w.x) * qq[1] + bf16lo(w.y) * qq[2] + bf16hi(w.y) * qq[3] + bf16lo(w.z) * qq[4] +
+           bf16hi(w.z) * qq[5] + bf16lo(w.w) * qq[6] + bf16hi(w.w) * qq[7];
+    }
+    s *= a.scale;
+    ap_sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_reduce<true>(mx, red);
+  float sum = 0.f;
+  for (int j = tid; j <= i; j += AP_THREADS) {
+    const float e = expf(ap_sc[j] - mx);
+    ap_sc[j] = e;
+    sum += e;
+  }
+  sum = block_reduce<false>(sum, red);
+  const float inv = 1.f / sum;
+  float* o = a.out + (((size_t)b * a.heads + h) * a.len + i) * a.len;
+  for (int j = tid; j < a.len; j += AP_THREADS) o[j] = j <= i ? ap_sc[j] * inv : 0.f;
+}
+
+cudaError_t launch_attn_probs(const AttnProbsArgs& a, cudaStream_t stream) {
+  if (a.B <= 0 || a.len <= 0) return cudaSuccess;
+  const size_t smem = (size_t)a.len * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(attn_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  attn_probs_kernel<<<dim3(a.len, a.heads, a.B), AP_THREADS, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
 }  // namespace vdd

@@ -196,9 +196,15 @@ class VddEngine:
     # ---- fused generate (the product path): host buffers in, host tokens out
     def generate(self, input_ids: torch.Tensor, images: Optional[torch.Tensor], use_unk: bool, use_none: bool,
                  params: _lib.vdd_sample_params, max_new_tokens: int, q: Optional[torch.Tensor] = None,
-                 scores_out: Optional[torch.Tensor] = None, images_cd: Optional[torch.Tensor] = None):
+                 scores_out: Optional[torch.Tensor] = None, images_cd: Optional[torch.Tensor] = None,
+                 attention_out: Optional[torch.Tensor] = None):
+        """attention_out: optional fp32 [B, heads, len, len] device tensor that receives the step-0 attention map of the
+        last layer of the main stream (vdd_set_attention_capture)."""
         ids = input_ids.detach().to("cpu", torch.int64).contiguous()
         B, T = ids.shape
+        if attention_out is not None:
+            _lib.check(self.lib.vdd_set_attention_capture(self.h, C.c_void_p(attention_out.data_ptr()), attention_out.numel()),
+                       "vdd_set_attention_capture")
         px = None
         if images is not None:
             # host (ideally pinned) pixels are copied by the library inside the call; device pixels are used in place

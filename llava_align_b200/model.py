@@ -40,6 +40,30 @@ class GenerateOutput(dict):
     __getattr__ = dict.get
 
 
+class _StepAttentions(tuple):
+    """`attentions[step]`: HF returns one tensor per layer.  The fused kernels never materialise attention matrices; the
+    map the reference's drivers actually read -- step 0, LAST layer (`attentions[0][-1]`, llava_calibrate.py:180,
+    MME/run_llava.py:218) -- is computed after the prefill from the last layer's queries and K cache.  Any other entry
+    raises instead of returning something made up."""
+
+    def __new__(cls, step, num_layers, last_layer_map):
+        self = super().__new__(cls, ())
+        self._step, self._L, self._map = step, num_layers, last_layer_map
+        return self
+
+    def __len__(self):
+        return self._L
+
+    def __getitem__(self, i):
+        if isinstance(i, int) and (i == -1 or i == self._L - 1) and self._map is not None:
+            return self._map
+        raise NotImplementedError(f"attentions[{self._step}][{i}] is not materialised: only attentions[0][-1] (step 0, last layer, "
+                                  f"main stream) is available from the fused path")
+
+    def __iter__(self):
+        raise NotImplementedError("only attentions[0][-1] is materialised by the fused path")
+
+
 class _VisionTowerHandle:
     """What drivers touch on `model.get_vision_tower()` (llava_sampling.py:49-53)."""
 
@@ -132,8 +156,8 @@ class LlavaLlamaForCausalLM:
         # VDD/VCD is active iff images_cd is given or use_dd / use_dd_unk is set (vcd_sample.py:122-124,147)
         use_cd = images_cd is not None and has_image
         vdd = do_sample and vdd_sampler_installed() and bool(use_dd or use_dd_unk or use_cd)
-        if vdd and use_cd and (use_dd or use_dd_unk):
-            raise NotImplementedError("images_cd together with use_dd/use_dd_unk (vcd_sample.py:148,171-185) is not built")
+        # images_cd together with the debias flags: the engine applies the reference's precedence (vcd_sample.py:148 -- the cd
+        # forward replaces the unk stream; :171-185 -- the 'none' stream joins only when both flags are set)
         use_unk = bool(vdd and use_dd_unk)
         use_none = bool(vdd and use_dd)
         if do_sample:
@@ -153,13 +177,20 @@ class LlavaLlamaForCausalLM:
             q = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device).exponential_(1)
         want_scores = bool(opt["output_scores"] and opt["return_dict_in_generate"])
         scores_buf = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device) if want_scores else None
+        attn_buf = None
+        if opt["output_attentions"] and opt["return_dict_in_generate"]:
+            Tm = T + (self.vdd_config.num_patches - 1 if has_image else 0)
+            attn_buf = torch.empty(B, self.vdd_config.num_attention_heads, Tm, Tm, dtype=torch.float32, device=self.device)
         new_tokens, steps = self.engine.generate(input_ids, images if has_image else None, use_unk, use_none, params,
-                                                 max_new_tokens, q, scores_buf, images_cd if (vdd and use_cd) else None)
+                                                 max_new_tokens, q, scores_buf, images_cd if (vdd and use_cd) else None, attn_buf)
         seq = torch.cat([input_ids.to("cpu", torch.int64), new_tokens], dim=1).to(input_ids.device)
         if not opt["return_dict_in_generate"]:
             return seq
         out = GenerateOutput(sequences=seq)
         out["scores"] = tuple(scores_buf[i] for i in range(steps)) if want_scores else None
-        out["attentions"] = None  # per-step attention maps are not materialised by the fused kernels (scope table row f-1)
+        # vcd_sample.py:241-246: decoder_attentions of the MAIN stream, one entry per step
+        L = self.vdd_config.num_hidden_layers
+        out["attentions"] = (tuple(_StepAttentions(i, L, attn_buf if i == 0 else None) for i in range(steps))
+                             if attn_buf is not None else None)
         out["hidden_states"] = None
         return out

@@ -211,6 +211,22 @@ class OracleVDD:
         return out.logits[:, -1, :].float(), cache  # vcd_sample.py:119 (last position only)
 
     @torch.no_grad()
+    def first_step_attention(self, input_ids, images=None):
+        """`attentions[0][-1]` of the reference's generate(output_attentions=True) (vcd_sample.py:241-246, read at
+        llava_calibrate.py:180): post-softmax weights of the LAST layer for the main stream's prefill, [B, heads, len, len].
+        Runs on a deep copy of the module: under transformers 5.5 a forward that records attentions leaves state behind
+        that perturbs later forwards of the same module (see tests/golden/make_golden.py)."""
+        import copy
+        llama = copy.deepcopy(self.llama)
+        embed = llama.model.embed_tokens
+        if images is not None:
+            feats = encode_images(self.vision, self.projector, images, self.cfg.mm_vision_select_layer)
+            out = llama(inputs_embeds=splice_main(embed, input_ids, feats.to(self.dtype)), use_cache=True, output_attentions=True)
+        else:
+            out = llama(input_ids=input_ids, use_cache=True, output_attentions=True)
+        return out.attentions[-1].float()
+
+    @torch.no_grad()
     def generate(self, input_ids, images=None, images_cd=None, use_dd=False, use_dd_unk=False, cd_alpha=None, cd_beta=None,
                  temperature=None, top_k=None, top_p=None, max_new_tokens=16, do_sample=True,
                  output_scores=False, keep_stream_logits=False, q_list=None, eos_token_id="cfg",
@@ -232,7 +248,8 @@ class OracleVDD:
         cd_embeds = None
         if images_cd is not None and images is not None:
             # use_cd (vcd_sample.py:122,148-150): the contrast forward sees the same prompt with images_cd spliced in
-            assert not (use_dd or use_dd_unk), "restated for use_cd alone"
+            # With use_dd / use_dd_unk also set, the `if use_cd:` arm at vcd_sample.py:148 still wins the first contrast
+            # forward (the unk stream is never run); only when BOTH flags are set does :171-185 add the 'none' stream.
             feats_cd = encode_images(self.vision, self.projector, images_cd, cfg.mm_vision_select_layer)
             cd_embeds = splice_main(embed, input_ids, feats_cd.to(self.dtype))
         t["vision_s"] = time.perf_counter() - t0
@@ -263,6 +280,8 @@ class OracleVDD:
                     u, _ = self._forward(None, inputs_embeds=cd_embeds)
                 else:
                     u = l.clone()
+                if use_dd and use_dd_unk:  # vcd_sample.py:171-185: its own persistent kwargs => a real stream with its own cache
+                    d, caches["d"] = self._forward(caches["d"], input_ids=debias_ids(seq, "none") if first else last_tok)
             elif vdd:
                 # vcd_sample.py:151-169: the first contrast stream is 'unk' when use_dd_unk is set, else 'none'
                 if use_dd_unk:

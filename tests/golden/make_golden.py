@@ -131,7 +131,10 @@ def make_inputs(cfg, B, T, seed):
     return torch.from_numpy(ids), img
 
 
-def run_reference(ref_sample, model, ids, img, n_new, flags, sampler, eos, seed, img_cd=None):
+ATTN_CASES = ("both_greedy", "unk_batch2_greedy", "cd_both_greedy")  # cases that also pin attentions[0][-1]
+
+
+def run_reference(ref_sample, model, ids, img, n_new, flags, sampler, eos, seed, img_cd=None, want_attn=False):
     from transformers.generation.logits_process import (LogitsProcessorList, TemperatureLogitsWarper,
                                                         TopKLogitsWarper, TopPLogitsWarper)
 
@@ -158,9 +161,12 @@ def run_reference(ref_sample, model, ids, img, n_new, flags, sampler, eos, seed,
         out = ref_sample.sample(
             model, ids.clone(), logits_warper=warpers,
             stopping_criteria=MaxLength431(ids.shape[1] + n_new),
-            pad_token_id=model.config.pad_token_id, eos_token_id=eos, output_scores=True,
+            pad_token_id=model.config.pad_token_id, eos_token_id=eos, output_scores=True, output_attentions=want_attn,
             return_dict_in_generate=True, attention_mask=torch.ones_like(ids), images=img, images_cd=img_cd,
             use_cache=True, **flags)
+    if want_attn:
+        # what llava_calibrate.py:180 reads: step 0, last layer, main stream -> [B, heads, len, len]
+        return out.sequences, torch.stack(out.scores, dim=0), out["attentions"][0][-1].float()
     return out.sequences, torch.stack(out.scores, dim=0)  # [B,T+n], [n,B,V]
 
 
@@ -179,6 +185,10 @@ CASES = [
     # use_cd: images_cd = add_diffusion_noise(image, 500) (vcd_utils/vcd_add_noise.py), VCD baseline of the reference
     ("cd_greedy", 1, 12, 8, dict(use_dd=False, use_dd_unk=False, cd_alpha=1.0, cd_beta=0.1, use_cd=500), dict(top_k=1), None),
     ("cd_sample_batch2", 2, 12, 8, dict(use_dd=False, use_dd_unk=False, cd_alpha=0.5, cd_beta=0.2, use_cd=700), dict(top_p=0.9), None),
+    # images_cd together with the debias flags (vcd_sample.py:148 wins the first contrast forward; :171-185 adds 'none' when both are set)
+    ("cd_both_greedy", 1, 12, 8, dict(use_dd=True, use_dd_unk=True, cd_alpha=1.0, cd_beta=0.1, use_cd=500), dict(top_k=1), None),
+    ("cd_both_sample", 1, 12, 8, dict(use_dd=True, use_dd_unk=True, cd_alpha=0.5, cd_beta=0.1, use_cd=600), dict(temperature=0.8, top_k=20), None),
+    ("cd_unk_only_greedy", 1, 12, 8, dict(use_dd=False, use_dd_unk=True, cd_alpha=1.0, cd_beta=0.1, use_cd=500), dict(top_k=1), None),
 ]
 
 
@@ -206,6 +216,14 @@ def main():
             seq0, _ = run_reference(ref_sample, model, ids, img, n_new, flags, sampler, None, seed=7)
             eos = int(seq0[0, T + 2])
         seq, scores = run_reference(ref_sample, model, ids, img, n_new, flags, sampler, eos, seed=7, img_cd=img_cd)
+        if name in ATTN_CASES:
+            # Second run with output_attentions=True on a FRESH model: under transformers 5.5 a forward that records attentions
+            # leaves state behind that perturbs later forwards of the same module (observed: the next run's tokens change),
+            # so it must not share a model with the other cases.  Its own tokens must reproduce the first run.
+            fresh = build_reference_model(ref_llama, cfg, sd)
+            seq_a, _, attn = run_reference(ref_sample, fresh, ids, img, n_new, flags, sampler, eos, seed=7, img_cd=img_cd, want_attn=True)
+            assert torch.equal(seq_a, seq), name
+            out[f"{name}.attn0_last"] = attn.numpy()
         out[f"{name}.sequences"] = seq.numpy()
         out[f"{name}.scores"] = scores.float().numpy()
         meta.append(dict(name=name, B=B, T=T, n_new=n_new, flags=dict(flags, use_cd=img_cd is not None), sampler=sampler, eos=eos,

@@ -138,6 +138,37 @@ def test_generate_surface(engine_model):
     assert c1.shape == (1, 17) and torch.equal(c1[:, :12].cpu(), ids)
 
 
+ATTN_CASES = [c for c in META["cases"] if c["name"] + ".attn0_last" in DATA.files]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES, ids=[c["name"] for c in ATTN_CASES])
+def test_first_step_attention_matches_reference(engine_model, case):
+    """generate(output_attentions=True, return_dict_in_generate=True)['attentions'][0][-1] -- what llava_calibrate.py:180 reads --
+    against the map the UNMODIFIED reference returned (tests/golden).  bf16 q/k on our side: absolute tolerance on probabilities."""
+    cfg, m, oracle = engine_model
+    ids, img = make_inputs(cfg, case["B"], case["T"], case["input_seed"])
+    f = case["flags"]
+    if case["B"] > 1 and f.get("use_dd"):
+        pytest.skip("reference use_dd is B=1 only")
+    ref = torch.from_numpy(DATA[case["name"] + ".attn0_last"])
+    img_cd = torch.from_numpy(DATA[case["name"] + ".images_cd"]).cuda() if f.get("use_cd") else None
+    out = m.generate(ids.cuda(), images=img.cuda(), images_cd=img_cd, use_dd=f.get("use_dd"), use_dd_unk=f.get("use_dd_unk"),
+                     cd_alpha=f.get("cd_alpha"), cd_beta=f.get("cd_beta"), do_sample=True, top_k=1, max_new_tokens=3,
+                     output_attentions=True, output_scores=True, return_dict_in_generate=True, eos_token_id=None)
+    att = out["attentions"]
+    assert len(att) == 3 and len(att[0]) == cfg.num_hidden_layers
+    a = att[0][-1].cpu()
+    assert a.shape == ref.shape
+    assert (a - ref).abs().max().item() < 2e-2, (a - ref).abs().max().item()
+    assert torch.allclose(a.sum(-1), torch.ones_like(a.sum(-1)), atol=1e-4)
+    assert torch.equal(torch.triu(a[0, 0], 1), torch.zeros_like(a[0, 0]))
+    torch.mean(a, dim=1).squeeze()  # what the driver does with it (llava_calibrate.py:182)
+    with pytest.raises(NotImplementedError):
+        att[1][-1]
+    with pytest.raises(NotImplementedError):
+        att[0][0]
+
+
 @pytest.mark.parametrize("B,use_unk,use_none,with_image,T", [(2, True, True, True, 10), (3, True, True, True, 9),
                                                             (4, True, False, True, 7), (1, False, False, False, 5),
                                                             (2, True, False, False, 6), (5, True, True, True, 4)])

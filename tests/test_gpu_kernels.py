@@ -183,3 +183,46 @@ def test_gemm_epilogues(M, N, K):
     exp = torch.zeros(M, N, device="cuda")
     exp[rm[1:].long()] = ref[1:]
     torch.testing.assert_close(out, exp, **tol)
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 skinny (stream-K) decode GEMM
+@pytest.mark.parametrize("R", [9, 16, 33, 96, 130, 192, 256])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (12288, 4096), (4096, 11008), (1000, 1376), (256, 64), (32000, 512)])
+def test_skinny_gemm_epilogues(R, N, K):
+    """Rows on both sides of the TMEM double-buffer switch (R <= 128 / > 128); N and K off the 256 / 64 tile; tiles owned
+    by one CTA and tiles shared by many (o_proj / down_proj shapes: 16 tiles over 148 SMs)."""
+    L = _lib()
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(R * 7 + N + K)
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    x = torch.randn(R, K, device="cuda", generator=g).bfloat16()
+    ref = x.float() @ W.float().T
+    tol = dict(rtol=2e-3, atol=2e-3)
+    out = torch.full((R, N), 7.0, device="cuda")
+    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), R, N, K, 0, _ptr(out), None, N, _stream()), "skinny f32")
+    torch.testing.assert_close(out, ref, **tol)
+    out_b = torch.full((R, N), 7.0, device="cuda")
+    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), R, N, K, 0, _ptr(out_b), None, N, _stream()), "skinny f32 again")
+    assert torch.equal(out, out_b), "split tiles must reduce in a fixed order"
+    base = torch.randn(R, N, device="cuda", generator=g)
+    out2 = base.clone()
+    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), R, N, K, 1, _ptr(out2), None, N, _stream()), "skinny add")
+    torch.testing.assert_close(out2, base + ref, **tol)
+    oh = torch.zeros(R, N // 2, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), R, N, K, 5, None, _ptr(oh), N // 2, _stream()), "skinny swiglu")
+    torch.testing.assert_close(oh.float(), torch.nn.functional.silu(ref[:, 0::2]) * ref[:, 1::2], rtol=1e-2, atol=1e-2)
+
+
+def test_skinny_gemm_rows_do_not_depend_on_batch():
+    """A row's result is bit-identical whatever other rows share the launch (the stream-K cut depends on N, K and the grid only)."""
+    L = _lib()
+    lib = L.load()
+    N, K = 4096, 4096
+    g = torch.Generator(device="cuda").manual_seed(5)
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    x = torch.randn(96, K, device="cuda", generator=g).bfloat16()
+    o96 = torch.zeros(96, N, device="cuda")
+    o20 = torch.zeros(20, N, device="cuda")
+    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), 96, N, K, 0, _ptr(o96), None, N, _stream()), "skinny 96")
+    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x[:20].contiguous()), 20, N, K, 0, _ptr(o20), None, N, _stream()), "skinny 20")
+    assert torch.equal(o96[:20], o20)

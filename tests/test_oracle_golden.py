@@ -34,6 +34,21 @@ def test_oracle_matches_reference(case):
     np.testing.assert_allclose(got[fin], ref_scores[fin], rtol=1e-4, atol=1e-4)
 
 
+ATTN_CASES = [c for c in META["cases"] if c["name"] + ".attn0_last" in DATA.files]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES, ids=[c["name"] for c in ATTN_CASES])
+def test_oracle_first_step_attention_matches_reference(case):
+    """attentions[0][-1] (llava_calibrate.py:180): step 0, last layer, main stream, as returned by the unmodified reference."""
+    cfg, sd, oracle = tiny_model(META["weight_seed"])
+    ids, img = make_inputs(cfg, case["B"], case["T"], case["input_seed"])
+    ref = DATA[case["name"] + ".attn0_last"]
+    got = oracle.first_step_attention(ids, img).numpy()
+    assert got.shape == ref.shape == (case["B"], cfg.num_attention_heads, case["T"] + cfg.num_patches - 1, case["T"] + cfg.num_patches - 1)
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+    assert np.all(np.triu(got[0, 0], 1) == 0)  # causal: nothing above the diagonal
+
+
 def test_multinomial_is_exponential_race():
     """Appendix A Q6: torch.multinomial(p,1) == argmax(p / Exp(1)) drawn from the same generator state.
     The CUDA sampler relies on it: it receives q from torch and returns argmax(p/q)."""
