@@ -316,10 +316,9 @@ __global__ void __cluster_dims__(1, DC_CL, 1) __launch_bounds__(DA_THREADS, 6) d
 // through a 3-stage shared-memory ring filled by 1-D bulk copies (cp.async.bulk + mbarrier; a head's tokens are
 // contiguous, 64 tokens = 16 KB of K and 16 KB of V per stage), so ~190 KB per SM are in flight with no register
 // staging.  Per-token arithmetic, the group merge and the split merge are those of decode_attn_kernel.
-constexpr int DS_STAGES = 3;
 constexpr int DS_TOK = 64;                         // tokens per stage
 constexpr int DS_STAGE_BYTES = DS_TOK * DA_D * 2;  // 16 KB (K) and the same again for V
-constexpr int DS_SMEM = DS_STAGES * 2 * DS_STAGE_BYTES + 128;
+constexpr int ds_smem_bytes(int stages) { return stages * 2 * DS_STAGE_BYTES + 128; }
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -327,7 +326,10 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                : "memory");
 }
 
-__global__ void __launch_bounds__(DA_THREADS, 2) decode_attn_stream_kernel(const DecodeAttnArgs a) {
+// DS_STAGES = 3: 96 KB ring, two CTAs per SM; DS_STAGES = 2: 64 KB ring, three CTAs per SM (more CTAs to overlap each other's
+// start-up and merge latencies; same bytes in flight per SM).
+template <int DS_STAGES>
+__global__ void __launch_bounds__(DA_THREADS, DS_STAGES == 2 ? 3 : 2) decode_attn_stream_kernel(const DecodeAttnArgs a) {
   extern __shared__ __align__(128) unsigned char ds_smem[];
   __shared__ float q_s[DA_D];
   __shared__ __align__(16) __nv_bfloat16 knew_s[DA_D];
@@ -371,7 +373,8 @@ __global__ void __launch_bounds__(DA_THREADS, 2) decode_attn_stream_kernel(const
   if (tid == 0)
     for (int c = 0; c < nst && c < DS_STAGES; ++c) issue(c);
   pdl_wait();
-  pdl_launch_dependents();
+  // No early griddepcontrol.launch_dependents here: this grid runs ~10 waves of CTAs, and dependents released early would sit
+  // in their own dependency wait holding shared memory the later waves need (measured: 7.03 -> 6.91 ms per step, config 3).
   {
     const float* qkv = a.qkv + (size_t)r * 3 * Hl;
     const int i = tid & 63;
@@ -511,9 +514,11 @@ __global__ void __launch_bounds__(DA_THREADS, 2) decode_attn_stream_kernel(const
 
 cudaError_t launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t stream) {
   if (a.item_row && a.n_items > 0) {  // streaming kernel over the (row, split) work table
+    static const int stages = (getenv("VDD_ATTN_STAGES") && atoi(getenv("VDD_ATTN_STAGES")) == 3) ? 3 : 2;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t ce = cudaFuncSetAttribute(decode_attn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM);
+      cudaError_t ce = cudaFuncSetAttribute(decode_attn_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds_smem_bytes(2));
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(decode_attn_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ds_smem_bytes(3));
       if (ce != cudaSuccess) return ce;
       attr_set = true;
     }
@@ -521,14 +526,14 @@ cudaError_t launch_decode_attn(const DecodeAttnArgs& a, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(a.heads, a.n_items);
     cfg.blockDim = dim3(DA_THREADS);
-    cfg.dynamicSmemBytes = DS_SMEM;
+    cfg.dynamicSmemBytes = ds_smem_bytes(stages);
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, decode_attn_stream_kernel, a);
+    return stages == 3 ? cudaLaunchKernelEx(&cfg, decode_attn_stream_kernel<3>, a) : cudaLaunchKernelEx(&cfg, decode_attn_stream_kernel<2>, a);
   }
 
   // Measured on B200 (bench.py, config 2): global-partials kernel 2.853 ms per decode step, cluster kernel 3.085 ms --

@@ -11,6 +11,8 @@ __global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(const float* __restri
                                                           float eps, __nv_bfloat16* __restrict__ out, int H,
                                                           const int32_t* __restrict__ row_idx) {
   __shared__ float red[33];
+  pdl_wait();  // no-op unless launched with programmatic stream serialization (decode chain)
+  pdl_launch_dependents();
   const int row = blockIdx.x;
   const float* xr = x + (size_t)(row_idx ? row_idx[row] : row) * H;
   float ss = 0.f;
@@ -29,9 +31,84 @@ __global__ void __launch_bounds__(256) rmsnorm_bf16_kernel(const float* __restri
   }
 }
 cudaError_t launch_rmsnorm_bf16(const float* x, const void* w, float eps, void* out, int rows, int H,
-                                const int32_t* row_idx, cudaStream_t stream) {
+                                const int32_t* row_idx, cudaStream_t stream, bool pdl) {
   if (rows <= 0) return cudaSuccess;
-  rmsnorm_bf16_kernel<<<rows, 256, 0, stream>>>(x, (const __nv_bfloat16*)w, eps, (__nv_bfloat16*)out, H, row_idx);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(rows);
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, rmsnorm_bf16_kernel, x, (const __nv_bfloat16*)w, eps, (__nv_bfloat16*)out, H, row_idx);
+}
+
+// Decode with many rows: the split-K planes of a residual GEMM are summed into the residual stream (plane order =>
+// deterministic) and the NEXT RMSNorm is applied in the same pass: resid[r] += sum_z ws[z][r];  out[r] = bf16(norm(resid[r]) * w).
+// splits == 0: the GEMM already accumulated into resid, only the norm remains.
+__global__ void __launch_bounds__(256) reduce_rmsnorm_kernel(float* __restrict__ resid, const float* __restrict__ ws, int splits,
+                                                             int64_t plane_stride, const __nv_bfloat16* __restrict__ w, float eps,
+                                                             __nv_bfloat16* __restrict__ out, int H) {
+  __shared__ float red[33];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x;
+  float* xr = resid + (size_t)row * H;
+  const float* wr = ws + (size_t)row * H;
+  float ss = 0.f;
+  for (int k = threadIdx.x * 4; k < H; k += 256 * 4) {
+    float4 a = *reinterpret_cast<const float4*>(xr + k);
+    for (int z = 0; z < splits; ++z) {
+      const float4 b = __ldcg(reinterpret_cast<const float4*>(wr + (int64_t)z * plane_stride + k));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (splits > 0) *reinterpret_cast<float4*>(xr + k) = a;
+    ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+  }
+  const float rstd = rsqrtf(block_reduce<false>(ss, red) / (float)H + eps);
+  for (int k = threadIdx.x * 4; k < H; k += 256 * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + k);  // this thread's own stores
+    const uint2 wv = *reinterpret_cast<const uint2*>(w + k);
+    uint2 o;
+    o.x = pack_bf16(v.x * rstd * bf16lo(wv.x), v.y * rstd * bf16hi(wv.x));
+    o.y = pack_bf16(v.z * rstd * bf16lo(wv.y), v.w * rstd * bf16hi(wv.y));
+    *reinterpret_cast<uint2*>(out + (size_t)row * H + k) = o;
+  }
+}
+cudaError_t launch_reduce_rmsnorm(float* resid, const float* ws, int splits, int rows, int H, const void* w, float eps, void* out,
+                                  cudaStream_t stream, bool pdl) {
+  if (rows <= 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(rows);
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, reduce_rmsnorm_kernel, resid, ws, splits, (int64_t)rows * H, (const __nv_bfloat16*)w, eps,
+                            (__nv_bfloat16*)out, H);
+}
+
+// B operand of a row-scaled projection (decode_gemm.cu): out = bf16(x * g); the 1/rms factor is applied by the consumer.
+__global__ void __launch_bounds__(256) scale_rows_bf16_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ g,
+                                                             __nv_bfloat16* __restrict__ out, int H) {
+  const float* xr = x + (size_t)blockIdx.x * H;
+  for (int k = threadIdx.x * 4; k < H; k += 256 * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + k);
+    const uint2 wv = *reinterpret_cast<const uint2*>(g + k);
+    uint2 o;
+    o.x = pack_bf16(v.x * bf16lo(wv.x), v.y * bf16hi(wv.x));
+    o.y = pack_bf16(v.z * bf16lo(wv.y), v.w * bf16hi(wv.y));
+    *reinterpret_cast<uint2*>(out + (size_t)blockIdx.x * H + k) = o;
+  }
+}
+cudaError_t launch_scale_rows_bf16(const float* x, const void* g, void* out, int rows, int H, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  scale_rows_bf16_kernel<<<rows, 256, 0, stream>>>(x, (const __nv_bfloat16*)g, (__nv_bfloat16*)out, H);
   return cudaGetLastError();
 }
 

@@ -99,8 +99,8 @@ struct vdd_engine {
   int D = 128, heads_l = 0, Hl = 0, Il = 0, Vl = 0, NP = 0, Kpad = 0, VD = 64;
   int num_sms = 148;
   bool use_pdl = true, use_graph = true, use_fused = true, use_skinny = true;
-  int* sk_counters = nullptr;  // per decode step: one zeroed counter block per skinny GEMM launch
-  int sk_launch = 0;
+  int* sk_counters = nullptr;  // per decode step: one zeroed block per skinny-chain launch (SK_BLOCK_INTS)
+  float* sk_inv_rms = nullptr; // [launch][4][256] row scales
   // weights
   void* arena = nullptr;
   size_t arena_bytes = 0;
@@ -435,12 +435,15 @@ static int tp_allreduce_add(vdd_engine* e, float* partial, float* resid, int64_t
 }
 
 static int do_gemm(vdd_engine* e, const void* a, const void* w, int M, int N, int K, int mode, const void* bias,
-                   const int32_t* row_map, float* of32, void* obf16, int64_t ldc, cudaStream_t st) {
+                   const int32_t* row_map, float* of32, void* obf16, int64_t ldc, cudaStream_t st, bool pdl = false,
+                   int* defer_reduce = nullptr) {
   GemmArgs g{a, w, M, N, K, mode, bias, row_map, of32, obf16, ldc};
+  g.pdl = pdl;
+  g.defer_reduce = defer_reduce;
   if (mode == GEMM_OUT_ADD_F32 && M <= 128 && e->split_ws.p) {  // decode with > 8 fused rows: deterministic split-K
     g.split_ws = (float*)e->split_ws.p;
     g.split_ws_bytes = e->split_ws.bytes;
-    e->launches++;
+    if (!defer_reduce) e->launches++;
   }
   cudaError_t ce = launch_gemm(g, st);
   e->launches++;
@@ -448,15 +451,35 @@ static int do_gemm(vdd_engine* e, const void* a, const void* w, int M, int N, in
     return fail(VDD_ERR_CUDA, "gemm M=%d N=%d K=%d: %s %s", M, N, K, cudaGetErrorString(ce), gemm_init_error() ? gemm_init_error() : "");
   return VDD_OK;
 }
-constexpr int SK_CNT_STRIDE = 256;  // counters per skinny GEMM launch (>= N/256 tiles of any projection)
-static int do_skinny(vdd_engine* e, const void* x, const void* w, int R, int N, int K, int mode, float* of32, void* obf16, int64_t ld,
-                     cudaStream_t st) {
-  if (skinny_gemm_tiles(N) > SK_CNT_STRIDE) return fail(VDD_ERR_UNSUPPORTED, "skinny gemm: N=%d too wide", N);
-  SkinnyArgs a{w, x, R, N, K, mode, of32, obf16, ld, (float*)e->sk_ws.p, e->sk_ws.bytes, e->sk_counters + (size_t)e->sk_launch * SK_CNT_STRIDE};
-  e->sk_launch++;
-  cudaError_t ce = launch_skinny_gemm(a, e->num_sms, e->use_pdl, st);
+// Zero-on-entry state of the skinny-GEMM chain launches of ONE decode step (cleared by a single memset per step):
+// launch li (0 = first layer's qkv, 1 + l = chain of layer l) owns a block of SK_BLOCK_INTS ints:
+//   [0, 4*SK_CNT_STRIDE)  tile counters of its (up to) four projections
+//   [.., +4)              grid barriers        [.., +4) row-statistic counters
+constexpr int SK_CNT_STRIDE = 256;  // >= N/256 tiles of any projection
+constexpr int SK_BLOCK_INTS = 4 * SK_CNT_STRIDE + 8;
+static SkinnyArgs sk_args(const void* x, const void* w, int N, int K, int mode, float* of32, void* obf16, int64_t ld, int64_t ld_bf16) {
+  SkinnyArgs a{};
+  a.w = w; a.x = x; a.N = N; a.K = K; a.epilogue = mode; a.out_f32 = of32; a.out_bf16 = obf16; a.ld = ld; a.ld_bf16 = ld_bf16;
+  return a;
+}
+// chain launch number `li` of the current decode step: wires the zeroed counters / barriers / scratch of its block
+static int do_skinny_chain(vdd_engine* e, SkinnyChain& ch, int li, cudaStream_t st) {
+  int* blk = e->sk_counters + (size_t)li * SK_BLOCK_INTS;
+  for (int q = 0; q < ch.n; ++q) {
+    if (skinny_gemm_tiles(ch.ph[q].N) > SK_CNT_STRIDE) return fail(VDD_ERR_UNSUPPORTED, "skinny gemm: N=%d too wide", ch.ph[q].N);
+    ch.ph[q].counters = blk + q * SK_CNT_STRIDE;
+    if (ch.ph[q].rs_x) {
+      ch.ph[q].norm_counter = blk + 4 * SK_CNT_STRIDE + 4 + q;
+      ch.ph[q].inv_rms = e->sk_inv_rms + ((size_t)li * 4 + q) * 256;
+    }
+  }
+  ch.R = e->R;
+  ch.ws = (float*)e->sk_ws.p;
+  ch.ws_bytes = e->sk_ws.bytes;
+  ch.barrier = (unsigned*)(blk + 4 * SK_CNT_STRIDE);
+  cudaError_t ce = launch_skinny_chain(ch, e->num_sms, e->use_pdl, st);
   e->launches++;
-  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm R=%d N=%d K=%d: %s", R, N, K, cudaGetErrorString(ce));
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny chain (R=%d, %d projections): %s", e->R, ch.n, cudaGetErrorString(ce));
   return VDD_OK;
 }
 #define RC(x)               \
@@ -657,13 +680,16 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   RC(ensure(e, e->kv, (size_t)2 * L * kv_total * 2));
   RC(ensure(e, e->logits, (size_t)R * c.vocab_size * 4));
   if (R > 8 && R <= 128) RC(ensure(e, e->split_ws, (size_t)8 * R * H * 4));
-  if (R > 8 && R <= 256 && e->use_skinny) {
+  e->sk_counters = nullptr;
+  if (R > 8 && R <= 256 && e->use_skinny && c.tp_size == 1) {
     size_t ws = 0;
     const int shapes[5][2] = {{3 * Hl, H}, {H, Hl}, {2 * Il, H}, {H, Il}, {e->Vl, H}};
     for (auto& sh : shapes) ws = std::max(ws, skinny_gemm_ws_bytes(R, sh[0], sh[1], e->num_sms));
     RC(ensure(e, e->sk_ws, ws));
-    RC(ensure(e, e->sk_cnt, (size_t)(4 * L + 1) * SK_CNT_STRIDE * 4));
+    const size_t cnt_bytes = align_up((size_t)(L + 1) * SK_BLOCK_INTS * 4, 256);
+    RC(ensure(e, e->sk_cnt, cnt_bytes + (size_t)(L + 1) * 4 * 256 * 4));
     e->sk_counters = (int*)e->sk_cnt.p;
+    e->sk_inv_rms = (float*)((char*)e->sk_cnt.p + cnt_bytes);
   }
   if (c.tp_size > 1) {
     RC(ensure(e, e->logits_tp, (size_t)R * c.vocab_size * 4));
@@ -841,20 +867,32 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     return g;
   };
   if (fused) CK(cudaMemsetAsync(e->d_bar, 0, (size_t)(L + 2) * 4 * 4, st));
-  const bool skinny = R > 8 && R <= 256 && e->use_skinny && e->sk_counters;  // stream-K tcgen05 kernel instead of the square-tile GEMM
-  if (skinny) {
-    e->sk_launch = 0;
-    CK(cudaMemsetAsync(e->sk_counters, 0, (size_t)(4 * L + 1) * SK_CNT_STRIDE * 4, st));
-  }
+  // 8 < R <= 256 on one GPU: stream-K tcgen05 chain, one launch per layer (decode_gemm.cu), RMSNorm folded into the epilogues
+  const bool skinny = R > 8 && R <= 256 && e->use_skinny && e->sk_counters && !tp;
+  if (skinny) CK(cudaMemsetAsync(e->sk_counters, 0, (size_t)(L + 1) * SK_BLOCK_INTS * 4, st));
   auto gemm = [&](const void* x, const void* w, int N, int K, int mode, float* of32, void* obf16, int64_t ld) -> int {
-    if (skinny) return do_skinny(e, x, w, R, N, K, mode, of32, obf16, ld, st);
     return do_gemm(e, x, w, R, N, K, mode, nullptr, nullptr, of32, obf16, ld, st);
   };
   if (!projections_only) LK(e, launch_decode_embed(e->embed, tokens, e->resid_d, e->B, e->S, H, st));
   if (fused) LK(e, launch_gemv(qkv_args(0), e->num_sms, pdl, st));
+  if (skinny) {
+    // layer 0: qkv = (W (g .* resid)) / rms(resid); every later qkv rides at the end of the previous layer's chain
+    LK(e, launch_scale_rows_bf16(e->resid_d, e->lw[0].ln1, e->xn_d, R, H, st));
+    SkinnyChain ch{};
+    ch.n = 1;
+    ch.ph[0] = sk_args(e->xn_d, e->lw[0].wqkv, 3 * Hl, H, GEMM_OUT_F32, e->qkv_d, nullptr, 3 * Hl, 0);
+    ch.ph[0].rs_x = e->resid_d; ch.ph[0].rs_K = H; ch.ph[0].rs_eps = c.rms_eps;
+    RC(do_skinny_chain(e, ch, 0, st));
+  }
+  // 8 < R on one GPU, square-tile GEMMs: every launch of the layer is programmatically serialised (set-up overlaps the
+  // predecessor's tail), and the split-K reduction of o_proj / down_proj is folded into the RMSNorm pass that follows it
+  const bool wide = R > 8 && !tp && !skinny;
+  if (wide) LK(e, launch_rmsnorm_bf16(e->resid_d, e->lw[0].ln1, c.rms_eps, e->xn_d, R, H, nullptr, st, pdl));
   for (int l = 0; l < L; ++l) {
     const LayerW& w = e->lw[l];
-    if (!fused) {
+    if (wide) {
+      RC(do_gemm(e, e->xn_d, w.wqkv, R, 3 * Hl, H, GEMM_OUT_F32, nullptr, nullptr, e->qkv_d, nullptr, 3 * Hl, st, pdl));
+    } else if (!fused && !skinny) {
       if (R <= 8) {
         LK(e, launch_gemv(qkv_args(l), e->num_sms, pdl, st));
       } else {
@@ -887,6 +925,32 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
       LK(e, launch_gemv_chain(ch, e->num_sms, pdl, st));
       continue;
     }
+    if (skinny) {
+      const bool last = l + 1 == L;
+      SkinnyChain ch{};
+      ch.n = 4;
+      ch.ph[0] = sk_args(e->attn_d, w.wo, H, Hl, GEMM_OUT_RESID_XG, e->resid_d, e->xn_d, H, H);
+      ch.ph[0].g = w.ln2;
+      ch.ph[1] = sk_args(e->xn_d, w.wgu, 2 * Il, H, GEMM_OUT_SWIGLU, nullptr, e->h_d, 0, Il);
+      ch.ph[1].rs_x = e->resid_d; ch.ph[1].rs_K = H; ch.ph[1].rs_eps = c.rms_eps;
+      ch.ph[2] = sk_args(e->h_d, w.wdown, H, Il, GEMM_OUT_RESID_XG, e->resid_d, e->xn_d, H, H);
+      ch.ph[2].g = last ? e->final_norm : e->lw[l + 1].ln1;
+      ch.ph[3] = last ? sk_args(e->xn_d, e->lm_head, e->Vl, H, GEMM_OUT_F32, lg, nullptr, e->Vl, 0)
+                      : sk_args(e->xn_d, e->lw[l + 1].wqkv, 3 * Hl, H, GEMM_OUT_F32, e->qkv_d, nullptr, 3 * Hl, 0);
+      ch.ph[3].rs_x = e->resid_d; ch.ph[3].rs_K = H; ch.ph[3].rs_eps = c.rms_eps;
+      RC(do_skinny_chain(e, ch, 1 + l, st));
+      continue;
+    }
+    if (wide) {
+      int sp = 0;
+      RC(do_gemm(e, e->attn_d, w.wo, R, H, Hl, GEMM_OUT_ADD_F32, nullptr, nullptr, e->resid_d, nullptr, H, st, pdl, &sp));
+      LK(e, launch_reduce_rmsnorm(e->resid_d, (const float*)e->split_ws.p, sp, R, H, w.ln2, c.rms_eps, e->xn_d, st, pdl));
+      RC(do_gemm(e, e->xn_d, w.wgu, R, 2 * Il, H, GEMM_OUT_SWIGLU, nullptr, nullptr, nullptr, e->h_d, Il, st, pdl));
+      RC(do_gemm(e, e->h_d, w.wdown, R, H, Il, GEMM_OUT_ADD_F32, nullptr, nullptr, e->resid_d, nullptr, H, st, pdl, &sp));
+      LK(e, launch_reduce_rmsnorm(e->resid_d, (const float*)e->split_ws.p, sp, R, H, l + 1 < L ? e->lw[l + 1].ln1 : e->final_norm,
+                                  c.rms_eps, e->xn_d, st, pdl));
+      continue;
+    }
     float* o_dst = tp ? (float*)e->tp_tmp.p : e->resid_d;
     const int o_mode_v = tp ? GEMV_OUT_F32 : GEMV_OUT_ADD_RESID;
     const int o_mode_m = tp ? GEMM_OUT_F32 : GEMM_OUT_ADD_F32;
@@ -907,9 +971,11 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     }
     if (tp) RC(tp_allreduce_add(e, o_dst, e->resid_d, (int64_t)R * H, st));
   }
-  if (!fused) {
+  if (!fused && !skinny) {
     if (R <= 8) {
       LK(e, launch_gemv(head_args(), e->num_sms, pdl, st));
+    } else if (wide) {
+      RC(do_gemm(e, e->xn_d, e->lm_head, R, e->Vl, H, GEMM_OUT_F32, nullptr, nullptr, lg, nullptr, e->Vl, st, pdl));
     } else {
       LK(e, launch_rmsnorm_bf16(e->resid_d, e->final_norm, c.rms_eps, e->xn_d, R, H, nullptr, st));
       RC(gemm(e->xn_d, e->lm_head, e->Vl, H, GEMM_OUT_F32, lg, nullptr, e->Vl));
@@ -1252,32 +1318,77 @@ extern "C" int vdd_gemv(const void* w, const void* x_bf16, const float* x_resid,
   return VDD_OK;
 }
 static unsigned long long* g_sk_trace = nullptr;
+static float* g_sk_ws = nullptr;
+static size_t g_sk_ws_bytes = 0;
+static int* g_sk_cnt = nullptr;
+static int sk_test_scratch(size_t need) {
+  if (need > g_sk_ws_bytes) {
+    if (g_sk_ws) cudaFree(g_sk_ws);
+    g_sk_ws_bytes = 0;
+    if (cudaMalloc(&g_sk_ws, need) != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm scratch: out of memory");
+    g_sk_ws_bytes = need;
+  }
+  if (!g_sk_cnt && cudaMalloc(&g_sk_cnt, (SK_BLOCK_INTS + 4 * 256) * 4) != cudaSuccess)
+    return fail(VDD_ERR_CUDA, "skinny gemm counters: out of memory");
+  return VDD_OK;
+}
 extern "C" int vdd_skinny_gemm(const void* w, const void* x_bf16, int R, int N, int K, int epilogue, float* out_f32, void* out_bf16,
                                int64_t ld, void* stream_v) {
-  static float* ws = nullptr;
-  static size_t ws_bytes = 0;
-  static int* cnt = nullptr;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const size_t need = skinny_gemm_ws_bytes(R, N, K, sms);
-  if (need > ws_bytes) {
-    if (ws) cudaFree(ws);
-    ws_bytes = 0;
-    if (cudaMalloc(&ws, need) != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm scratch: out of memory");
-    ws_bytes = need;
-  }
-  if (!cnt && cudaMalloc(&cnt, 4096 * 4) != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm counters: out of memory");
-  if (skinny_gemm_tiles(N) > 4096) return fail(VDD_ERR_UNSUPPORTED, "N too wide");
+  if (skinny_gemm_tiles(N) > SK_CNT_STRIDE) return fail(VDD_ERR_UNSUPPORTED, "N too wide");
+  RC(sk_test_scratch(skinny_gemm_ws_bytes(R, N, K, sms)));
   cudaStream_t st = (cudaStream_t)stream_v;
-  cudaMemsetAsync(cnt, 0, 4096 * 4, st);
-  SkinnyArgs a{w, x_bf16, R, N, K, epilogue, out_f32, out_bf16, ld, ws, ws_bytes, cnt};
-  a.trace = g_sk_trace;
-  cudaError_t ce = launch_skinny_gemm(a, sms, getenv("VDD_NO_PDL") == nullptr, st);
+  cudaMemsetAsync(g_sk_cnt, 0, SK_BLOCK_INTS * 4, st);
+  SkinnyChain ch{};
+  ch.R = R; ch.n = 1;
+  ch.ph[0] = sk_args(x_bf16, w, N, K, epilogue, out_f32, out_bf16, ld, ld);
+  ch.ph[0].counters = g_sk_cnt;
+  ch.ws = g_sk_ws; ch.ws_bytes = g_sk_ws_bytes; ch.barrier = nullptr; ch.trace = g_sk_trace;
+  cudaError_t ce = launch_skinny_chain(ch, sms, getenv("VDD_NO_PDL") == nullptr, st);
   if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm R=%d N=%d K=%d: %s", R, N, K, cudaGetErrorString(ce));
   return VDD_OK;
 }
-/* Debug: arm (device buffer of [grid][8] u64 globaltimer stamps) or disarm (NULL) tracing of vdd_skinny_gemm launches. */
+/* One decoder layer's projection chain for 8 < R <= 256 rows, stand-alone (tests / micro-benchmarks):
+ *   resid += attn . Wo^T;  h = SwiGLU(rmsnorm(resid; g2) . Wgu^T);  resid += h . Wdown^T;  out = rmsnorm(resid; g3) . Wnext^T
+ * xg [R,H] bf16 and h [R,I] bf16 are scratch.  Wgu rows interleave gate/up. */
+extern "C" int vdd_skinny_layer_chain(const void* attn_bf16, float* resid, const void* wo, const void* g2, const void* wgu, const void* wdown,
+                                      const void* g3, const void* wnext, int R, int H, int Hl, int I, int Nnext, float eps, void* xg_bf16,
+                                      void* h_bf16, float* out_f32, void* stream_v) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  size_t need = 0;
+  const int shapes[4][2] = {{H, Hl}, {2 * I, H}, {H, I}, {Nnext, H}};
+  for (auto& sh : shapes) {
+    if (skinny_gemm_tiles(sh[0]) > SK_CNT_STRIDE) return fail(VDD_ERR_UNSUPPORTED, "N too wide");
+    need = std::max(need, skinny_gemm_ws_bytes(R, sh[0], sh[1], sms));
+  }
+  RC(sk_test_scratch(need));
+  cudaStream_t st = (cudaStream_t)stream_v;
+  cudaMemsetAsync(g_sk_cnt, 0, SK_BLOCK_INTS * 4, st);
+  float* inv = (float*)(g_sk_cnt + SK_BLOCK_INTS);
+  SkinnyChain ch{};
+  ch.R = R; ch.n = 4;
+  ch.ph[0] = sk_args(attn_bf16, wo, H, Hl, GEMM_OUT_RESID_XG, resid, xg_bf16, H, H);
+  ch.ph[0].g = g2;
+  ch.ph[1] = sk_args(xg_bf16, wgu, 2 * I, H, GEMM_OUT_SWIGLU, nullptr, h_bf16, 0, I);
+  ch.ph[1].rs_x = resid; ch.ph[1].rs_K = H; ch.ph[1].rs_eps = eps;
+  ch.ph[2] = sk_args(h_bf16, wdown, H, I, GEMM_OUT_RESID_XG, resid, xg_bf16, H, H);
+  ch.ph[2].g = g3;
+  ch.ph[3] = sk_args(xg_bf16, wnext, Nnext, H, GEMM_OUT_F32, out_f32, nullptr, Nnext, 0);
+  ch.ph[3].rs_x = resid; ch.ph[3].rs_K = H; ch.ph[3].rs_eps = eps;
+  for (int q = 0; q < 4; ++q) {
+    ch.ph[q].counters = g_sk_cnt + q * SK_CNT_STRIDE;
+    if (ch.ph[q].rs_x) { ch.ph[q].norm_counter = g_sk_cnt + 4 * SK_CNT_STRIDE + 4 + q; ch.ph[q].inv_rms = inv + q * 256; }
+  }
+  ch.ws = g_sk_ws; ch.ws_bytes = g_sk_ws_bytes; ch.barrier = (unsigned*)(g_sk_cnt + 4 * SK_CNT_STRIDE); ch.trace = g_sk_trace;
+  cudaError_t ce = launch_skinny_chain(ch, sms, getenv("VDD_NO_PDL") == nullptr, st);
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny layer chain R=%d: %s", R, cudaGetErrorString(ce));
+  return VDD_OK;
+}
+/* Debug: arm (device buffer of [grid][16] u64 globaltimer stamps) or disarm (NULL) tracing of vdd_skinny_gemm launches. */
 extern "C" int vdd_skinny_gemm_trace(unsigned long long* dev_buf) {
   g_sk_trace = dev_buf;
   return VDD_OK;

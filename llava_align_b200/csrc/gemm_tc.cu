@@ -67,6 +67,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Set-up above overlaps the tail of the previous kernel when launched with programmatic stream serialization (decode);
+  // everything below may read what that kernel wrote.  No-op for ordinary launches.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -235,9 +239,19 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   grid.z = ep.splits;
   if (ep.splits > 1) ep.out_f32 = a.split_ws;
-  gemm_tc_kernel<<<grid, GM_THREADS, GM_SMEM, stream>>>(ta, tb, ep);
-  cudaError_t le = cudaGetLastError();
-  if (le != cudaSuccess || ep.splits == 1) return le;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GM_THREADS);
+  cfg.dynamicSmemBytes = GM_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = a.pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, ta, tb, ep);
+  if (a.defer_reduce) *a.defer_reduce = ep.splits > 1 ? ep.splits : 0;
+  if (le != cudaSuccess || ep.splits == 1 || a.defer_reduce) return le;
   return launch_reduce_splits(a.out_f32, a.split_ws, (int64_t)a.M * a.ldc, ep.splits, stream);
 }
 

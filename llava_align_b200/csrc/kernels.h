@@ -74,7 +74,8 @@ enum GemmEpilogue {
   GEMM_OUT_BF16 = 2,       // out_bf16 = acc (+bias)
   GEMM_OUT_BF16_QGELU = 3, // quick_gelu(acc+bias)   (CLIP MLP)
   GEMM_OUT_BF16_GELU = 4,  // gelu_erf(acc+bias)     (mm_projector)
-  GEMM_OUT_SWIGLU = 5      // out_bf16[row, col/2] = silu(acc[2i]) * acc[2i+1]  (interleaved gate/up)
+  GEMM_OUT_SWIGLU = 5,     // out_bf16[row, col/2] = silu(acc[2i]) * acc[2i+1]  (interleaved gate/up)
+  GEMM_OUT_RESID_XG = 6    // skinny chain only: out_f32 += acc; out_bf16 = bf16(out_f32 * g[col])  (residual + next norm's operand)
 };
 struct GemmArgs {
   const void* a;  // bf16 [M, K] row-major (lda = K)
@@ -88,25 +89,40 @@ struct GemmArgs {
   int64_t ldc;
   float* split_ws = nullptr;  // optional [splits, M, ldc] fp32 scratch: lets a decode-sized ADD GEMM split K deterministically
   size_t split_ws_bytes = 0;
+  bool pdl = false;           // launch with programmatic stream serialization (the kernel waits before touching dependent data)
+  int* defer_reduce = nullptr;  // non-null: leave the split-K planes in split_ws and report their number here (0 = accumulated
+                                // directly); the caller folds the reduction into its next pass (launch_reduce_rmsnorm)
 };
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
 const char* gemm_init_error();
 
-// ---------------------------------------------------------------- tcgen05 skinny GEMM for decode (8 < R <= 256 rows)
-// out[r, n] (op)= sum_k x[r, k] * w[n, k]; epilogue = GEMM_OUT_F32 | GEMM_OUT_ADD_F32 | GEMM_OUT_SWIGLU.
+// ---------------------------------------------------------------- tcgen05 skinny GEMM chain for decode (8 < R <= 256 rows)
+// One projection: out[r, n] (op)= sum_k x[r, k] * w[n, k], optionally scaled per row by 1/rms(rs_x[r, :]) (the RMSNorm of
+// the consumer, see decode_gemm.cu).  Up to four dependent projections run in one launch.
 struct SkinnyArgs {
   const void* w;  // bf16 [N, K]
   const void* x;  // bf16 [R, K]
-  int R, N, K, epilogue;
-  float* out_f32;
-  void* out_bf16;
-  int64_t ld;
-  float* ws;        // fp32 scratch for tiles shared by several CTAs (skinny_gemm_ws_bytes)
-  size_t ws_bytes;
-  int* counters;    // [skinny_gemm_tiles(N)] zero on entry (left non-zero)
-  unsigned long long* trace = nullptr;  // debug: [grid][8] globaltimer stamps
+  int N, K, epilogue;  // GEMM_OUT_F32 | GEMM_OUT_ADD_F32 | GEMM_OUT_SWIGLU | GEMM_OUT_RESID_XG
+  float* out_f32;      // F32: store; ADD_F32 / RESID_XG: +=   (row pitch ld)
+  void* out_bf16;      // SWIGLU: [R, N/2]; RESID_XG: bf16((out_f32 after the add) * g)   (row pitch ld_bf16)
+  int64_t ld, ld_bf16;
+  const void* g = nullptr;        // RESID_XG: bf16 [N] weight of the next RMSNorm
+  const float* rs_x = nullptr;    // row scale source [R, rs_K] fp32, or null
+  int rs_K = 0;
+  float rs_eps = 0.f;
+  float* inv_rms = nullptr;       // [R] scratch
+  int* norm_counter = nullptr;    // zero on entry
+  int* counters = nullptr;        // [skinny_gemm_tiles(N)] zero on entry (left non-zero)
 };
-cudaError_t launch_skinny_gemm(const SkinnyArgs& a, int num_sms, bool pdl, cudaStream_t stream);
+struct SkinnyChain {
+  int R, n;
+  SkinnyArgs ph[4];
+  float* ws;          // fp32 scratch for tiles shared by several CTAs: max over phases of skinny_gemm_ws_bytes
+  size_t ws_bytes;
+  unsigned* barrier;  // [n - 1] zero on entry
+  unsigned long long* trace = nullptr;  // debug: [grid][16] globaltimer stamps
+};
+cudaError_t launch_skinny_chain(const SkinnyChain& ch, int num_sms, bool pdl, cudaStream_t stream);
 size_t skinny_gemm_ws_bytes(int R, int N, int K, int num_sms);
 int skinny_gemm_tiles(int N);
 
@@ -166,7 +182,10 @@ cudaError_t launch_attn_probs(const AttnProbsArgs& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------- element-wise / glue
 cudaError_t launch_rmsnorm_bf16(const float* x, const void* w_bf16, float eps, void* out_bf16, int rows, int H,
-                                const int32_t* row_idx, cudaStream_t stream);
+                                const int32_t* row_idx, cudaStream_t stream, bool pdl = false);
+// resid[r] += sum_z ws[z][r] (split-K planes of a residual GEMM, plane pitch rows*H), then out[r] = bf16(rmsnorm(resid[r]) * w)
+cudaError_t launch_reduce_rmsnorm(float* resid, const float* ws, int splits, int rows, int H, const void* w_bf16, float eps,
+                                  void* out_bf16, cudaStream_t stream, bool pdl);
 cudaError_t launch_layernorm(const float* x, const void* w_bf16, const void* b_bf16, float eps, void* out_bf16,
                              float* out_f32, int rows, int H, const int32_t* row_idx, cudaStream_t stream);
 cudaError_t launch_embed_rows(const void* table_bf16, const int32_t* tok, const int32_t* img_row,
@@ -183,6 +202,7 @@ cudaError_t launch_decode_embed(const void* table_bf16, const int64_t* tokens, f
 cudaError_t launch_advance(int32_t* pos, int R, int32_t* step, cudaStream_t stream, int32_t* epoch = nullptr);  // pos[r] += 1, *step += 1, *epoch += 1
 cudaError_t launch_add_rows(float* dst, const float* src, int64_t n, cudaStream_t stream);
 cudaError_t launch_reduce_splits(float* dst, const float* ws, int64_t n, int splits, cudaStream_t stream);  // dst += sum_z ws[z]
+cudaError_t launch_scale_rows_bf16(const float* x, const void* g_bf16, void* out_bf16, int rows, int H, cudaStream_t stream);  // out = bf16(x * g)
 cudaError_t launch_cast_rows_bf16(const float* src, void* dst_bf16, int rows, int H, const int32_t* row_idx,
                                   cudaStream_t stream);
 

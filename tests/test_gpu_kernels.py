@@ -226,3 +226,49 @@ def test_skinny_gemm_rows_do_not_depend_on_batch():
     L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), 96, N, K, 0, _ptr(o96), None, N, _stream()), "skinny 96")
     L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x[:20].contiguous()), 20, N, K, 0, _ptr(o20), None, N, _stream()), "skinny 20")
     assert torch.equal(o96[:20], o20)
+
+
+def _layer_chain_case(R, H, Hl, I, Nn, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    mk = lambda n, k: (torch.randn(n, k, device="cuda", generator=g) / k ** 0.5).bfloat16()
+    wo, wd, wn = mk(H, Hl), mk(H, I), mk(Nn, H)
+    gate, up = mk(I, H), mk(I, H)
+    wgu = torch.stack([gate, up], dim=1).reshape(2 * I, H).contiguous()
+    g2 = (1 + 0.1 * torch.randn(H, device="cuda", generator=g)).bfloat16()
+    g3 = (1 + 0.1 * torch.randn(H, device="cuda", generator=g)).bfloat16()
+    attn = torch.randn(R, Hl, device="cuda", generator=g).bfloat16()
+    resid = torch.randn(R, H, device="cuda", generator=g) * 2
+    return wo, wgu, gate, up, wd, wn, g2, g3, attn, resid
+
+
+@pytest.mark.parametrize("R,H,Hl,I,Nn", [(96, 4096, 4096, 11008, 12288), (16, 4096, 4096, 11008, 32000), (9, 256, 256, 512, 768),
+                                         (130, 1024, 512, 1376, 1000), (48, 5120, 1280, 3456, 3840)])
+def test_skinny_layer_chain(R, H, Hl, I, Nn):
+    """One launch = o_proj + residual, RMSNorm + gate/up + SwiGLU, down_proj + residual, RMSNorm + next projection (HF
+    LlamaDecoderLayer order), vs torch fp32 on the same bf16 weights.  The chain keeps bf16(resid * g) as the GEMM operand and
+    scales the accumulator by 1/rms afterwards; torch normalises first: same maths, different rounding point."""
+    L = _lib()
+    lib = L.load()
+    wo, wgu, gate, up, wd, wn, g2, g3, attn, resid0 = _layer_chain_case(R, H, Hl, I, Nn, R + H + I)
+    eps = 1e-5
+    rms = lambda x, gw: x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * gw.float()
+    r1 = resid0 + attn.float() @ wo.float().T
+    x1 = rms(r1, g2)
+    h = torch.nn.functional.silu(x1 @ gate.float().T) * (x1 @ up.float().T)
+    r2 = r1 + h @ wd.float().T
+    out_ref = rms(r2, g3) @ wn.float().T
+    resid = resid0.clone()
+    xg = torch.empty(R, H, device="cuda", dtype=torch.bfloat16)
+    hb = torch.empty(R, I, device="cuda", dtype=torch.bfloat16)
+    out = torch.full((R, Nn), 7.0, device="cuda")
+    run = lambda rs, o: L.check(lib.vdd_skinny_layer_chain(_ptr(attn), _ptr(rs), _ptr(wo), _ptr(g2), _ptr(wgu), _ptr(wd), _ptr(g3),
+                                                           _ptr(wn), R, H, Hl, I, Nn, eps, _ptr(xg), _ptr(hb), _ptr(o), _stream()),
+                                "layer chain")
+    run(resid, out)
+    torch.testing.assert_close(hb.float(), h, rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(resid, r2, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(out, out_ref, rtol=3e-2, atol=3e-2)
+    # bit-identical run to run, and rows do not depend on the rows beside them
+    resid_b, out_b = resid0.clone(), torch.zeros_like(out)
+    run(resid_b, out_b)
+    assert torch.equal(out, out_b) and torch.equal(resid, resid_b)
