@@ -267,12 +267,12 @@ def main():
     reps = 1 if a.profile else 20
     fused_rows = 3 * B <= 8  # the GEMV chain is the R <= 8 path; larger batches decode through gemm_tc_kernel
     with torch.cuda.stream(eng.stream):
-        for _ in range(0 if (a.profile or not fused_rows) else 3):
+        for _ in range(0 if a.profile else 3):
             _lib.check(lib.vdd_bench_projection_chain(eng.h, eng.stream.cuda_stream), "chain")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng.launch_count(reset=True)
         e0.record(eng.stream)
-        for _ in range(reps if fused_rows else 0):
+        for _ in range(reps):
             _lib.check(lib.vdd_bench_projection_chain(eng.h, eng.stream.cuda_stream), "chain")
         e1.record(eng.stream)
     torch.cuda.synchronize()
@@ -296,9 +296,10 @@ def main():
                        f"({n_proj} projections, 13.21 GB of weights)"}
     # whole decode step against its own algorithmic bytes (weights once + KV of all rows + logits)
     if not fused_rows:
-        roofline = {"bound": "hbm", "kernel": "vdd::gemm_tc_kernel (decode with > 8 fused rows)", "achieved": None, "peak": peak,
-                    "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
-                    "how": "not timed separately at this batch; see decode_step for the whole step against its algorithmic bytes"}
+        roofline.update({"kernel": f"vdd::gemm_tc_kernel (tcgen05; decode projections of {3 * B} fused rows: qkv, o, gate_up, down per layer + "
+                                   f"lm_head, with the split-K reduce + RMSNorm passes between them)", "traffic": None,
+                         "how": f"CUDA events around {reps} back-to-back replays of one decode step's projection launches "
+                                f"({n_gemv} launches incl. {2 * L + 1} norm passes, 13.21 GB of weights)"})
     ctx_mid = (T + cfg.num_patches - 1) + T + (T - 1) + 3 * (n_new // 2)
     step_bytes = proj_bytes + B * ctx_mid * kv_tok + 3 * B * V * 4
     step_ms = tm["decode_ms"] / max(1, n_new - 1)

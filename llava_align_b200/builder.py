@@ -3,12 +3,12 @@ with the reference's signature and return tuple (reference experiments/llava/mod
 
 No checkpoint can be fetched offline, so two sources are supported:
   * "random:<name>[:seed]"  -- seeded random-init weights of the named architecture (llava-v1.5-7b / -13b / tiny);
-  * a local directory holding an HF LLaVA-1.5 checkpoint in safetensors shards (model.*, lm_head.*, vision tower).
+  * a local directory holding an HF LLaVA-1.5 checkpoint (config.json + *.safetensors or pytorch_model*.bin shards) whose
+    CLIP tower is found through `mm_vision_tower` / `vision_tower_path` (llava_align_b200/checkpoint.py).
 LoRA / 8-bit / 4-bit / MPT branches of the reference loader are out of scope.
 """
 from __future__ import annotations
 
-import glob
 import os
 
 import torch
@@ -36,7 +36,7 @@ def _load_random(model: LlavaLlamaForCausalLM, seed: int, exact: bool):
 
 
 def load_pretrained_model(model_path, model_base=None, model_name=None, load_8bit=False, load_4bit=False, device_map="auto",
-                          device="cuda", tp_size=1, tp_rank=0):
+                          device="cuda", tp_size=1, tp_rank=0, vision_tower_path=None):
     if load_8bit or load_4bit:
         raise NotImplementedError("bitsandbytes loading is outside the VDD path")
     dev = torch.device("cuda", torch.cuda.current_device()) if device == "cuda" else torch.device(device)
@@ -48,23 +48,21 @@ def load_pretrained_model(model_path, model_base=None, model_name=None, load_8bi
         model = LlavaLlamaForCausalLM(cfg, dev, tp_size, tp_rank)
         _load_random(model, seed, exact=cfg.name == "tiny")
     else:
-        from safetensors import safe_open  # local checkpoint directory
-        cfg = by_name(model_name or os.path.basename(str(model_path)))
+        # local checkpoint directory (reference builder.py:97-103,137-141): LLaVA shards + the CLIP tower they point at
+        from .checkpoint import config_from_hf, iter_checkpoint_tensors
+        cfg = config_from_hf(model_path, vision_tower_path)
         model = LlavaLlamaForCausalLM(cfg, dev, tp_size, tp_rank)
-        files = sorted(glob.glob(os.path.join(model_path, "*.safetensors")))
-        if not files:
-            raise FileNotFoundError(f"no *.safetensors under {model_path}")
-        for f in files:
-            with safe_open(f, framework="pt", device="cpu") as sf:
-                for k in sf.keys():
-                    model.engine.load_tensor(k, sf.get_tensor(k))
+        for name, t in iter_checkpoint_tensors(model_path, vision_tower_path):
+            model.engine.load_tensor(name, t)
         model.engine.check_complete()
         try:
             from transformers import AutoTokenizer, CLIPImageProcessor
+            from .checkpoint import find_vision_tower_dir, _read_json
             tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)
-            image_processor = CLIPImageProcessor.from_pretrained(model_path)
+            vdir = find_vision_tower_dir(model_path, _read_json(os.path.join(model_path, "config.json")), vision_tower_path)
+            image_processor = CLIPImageProcessor.from_pretrained(vdir or model_path)
             model.get_vision_tower().image_processor = image_processor
         except Exception:
-            pass
+            pass  # weights-only directories (tests) carry no tokenizer / preprocessor files
     context_len = getattr(model.config, "max_sequence_length", 2048)  # builder.py:143-146
     return tokenizer, model, image_processor, context_len

@@ -48,9 +48,12 @@ cudaError_t launch_rmsnorm_bf16(const float* x, const void* w, float eps, void* 
 // Decode with many rows: the split-K planes of a residual GEMM are summed into the residual stream (plane order =>
 // deterministic) and the NEXT RMSNorm is applied in the same pass: resid[r] += sum_z ws[z][r];  out[r] = bf16(norm(resid[r]) * w).
 // splits == 0: the GEMM already accumulated into resid, only the norm remains.
-__global__ void __launch_bounds__(256) reduce_rmsnorm_kernel(float* __restrict__ resid, const float* __restrict__ ws, int splits,
-                                                             int64_t plane_stride, const __nv_bfloat16* __restrict__ w, float eps,
-                                                             __nv_bfloat16* __restrict__ out, int H) {
+// 1024 threads per row: one float4 of the row per thread (H = 4096), so the residual and all split planes of a row are
+// requested at once -- the pass is a handful of dependent L2 round trips, not a bandwidth problem.
+constexpr int RR_THREADS = 1024;
+__global__ void __launch_bounds__(RR_THREADS) reduce_rmsnorm_kernel(float* __restrict__ resid, const float* __restrict__ ws, int splits,
+                                                                    int64_t plane_stride, const __nv_bfloat16* __restrict__ w, float eps,
+                                                                    __nv_bfloat16* __restrict__ out, int H) {
   __shared__ float red[33];
   pdl_wait();
   pdl_launch_dependents();
@@ -58,9 +61,20 @@ __global__ void __launch_bounds__(256) reduce_rmsnorm_kernel(float* __restrict__
   float* xr = resid + (size_t)row * H;
   const float* wr = ws + (size_t)row * H;
   float ss = 0.f;
-  for (int k = threadIdx.x * 4; k < H; k += 256 * 4) {
+  for (int k = threadIdx.x * 4; k < H; k += RR_THREADS * 4) {
     float4 a = *reinterpret_cast<const float4*>(xr + k);
-    for (int z = 0; z < splits; ++z) {
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {  // four planes in flight, added in plane order
+      const float4 b0 = __ldcg(reinterpret_cast<const float4*>(wr + (int64_t)z * plane_stride + k));
+      const float4 b1 = __ldcg(reinterpret_cast<const float4*>(wr + (int64_t)(z + 1) * plane_stride + k));
+      const float4 b2 = __ldcg(reinterpret_cast<const float4*>(wr + (int64_t)(z + 2) * plane_stride + k));
+      const float4 b3 = __ldcg(reinterpret_cast<const float4*>(wr + (int64_t)(z + 3) * plane_stride + k));
+      a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w;
+      a.x += b1.x; a.y += b1.y; a.z += b1.z; a.w += b1.w;
+      a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
+      a.x += b3.x; a.y += b3.y; a.z += b3.z; a.w += b3.w;
+    }
+    for (; z < splits; ++z) {
       const float4 b = __ldcg(reinterpret_cast<const float4*>(wr + (int64_t)z * plane_stride + k));
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
@@ -68,7 +82,7 @@ __global__ void __launch_bounds__(256) reduce_rmsnorm_kernel(float* __restrict__
     ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
   }
   const float rstd = rsqrtf(block_reduce<false>(ss, red) / (float)H + eps);
-  for (int k = threadIdx.x * 4; k < H; k += 256 * 4) {
+  for (int k = threadIdx.x * 4; k < H; k += RR_THREADS * 4) {
     const float4 v = *reinterpret_cast<const float4*>(xr + k);  // this thread's own stores
     const uint2 wv = *reinterpret_cast<const uint2*>(w + k);
     uint2 o;
@@ -82,7 +96,7 @@ cudaError_t launch_reduce_rmsnorm(float* resid, const float* ws, int splits, int
   if (rows <= 0) return cudaSuccess;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(rows);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(RR_THREADS);
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

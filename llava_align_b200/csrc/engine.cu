@@ -658,10 +658,11 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   std::vector<int32_t> item_row, item_split;
   e->attn_items = 0;
   e->attn_chunk = 0;
-  if (R > 8 && !getenv("VDD_ATTN_LEGACY")) {
+  const bool stream_small = getenv("VDD_ATTN_STREAM_SMALL") != nullptr;  // experiment: streaming kernel for R <= 8 too
+  if ((R > 8 || stream_small) && !getenv("VDD_ATTN_LEGACY")) {
     // measured on B200 (config 3, 96 rows, ms per decode step): 64-token kernel 8.51; chunk 128: 9.14, 512: 7.85, 1024: 7.40 --
     // one CTA per (row, head) up to 1024 tokens beats finer splits + merges even though main rows are 7x the debias rows
-    int chunk = getenv("VDD_ATTN_CHUNK") ? atoi(getenv("VDD_ATTN_CHUNK")) : 1024;
+    int chunk = getenv("VDD_ATTN_CHUNK") ? atoi(getenv("VDD_ATTN_CHUNK")) : (R > 8 ? 1024 : 128);
     if (chunk < 64 || chunk % 64) chunk = 1024;
     for (int q = 0; q < R; ++q)
       for (int sp = 0; sp * chunk < kv_cap[q]; ++sp) { item_row.push_back(q); item_split.push_back(sp); }

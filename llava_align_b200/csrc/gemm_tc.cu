@@ -12,16 +12,21 @@
 // residual add, SwiGLU over interleaved gate/up columns, row remap for the image splice) straight to global memory.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (one TMEM lane quadrant each).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vdd {
 
-constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 64, GM_STAGES = 3;  // 3 x 32 KB per CTA => two CTAs per SM: one's epilogue overlaps the other's main loop
+constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 64;
+// Ring depth (template parameter of the kernel):
+//   3 x 32 KB per CTA => two CTAs per SM, one's epilogue overlaps the other's main loop (prefill, ViT: many waves of tiles);
+//   6 x 32 KB, one CTA per SM, for grids that fit the machine in one wave anyway (decode with > 8 rows: 96-128 CTAs, each a
+//   pure weight stream) -- twice the bytes in flight per SM (measured 3.0 TB/s with 3 stages: latency-bound, not HBM-bound).
 constexpr int GM_THREADS = 192;
 constexpr int GM_STAGE_BYTES = (GM_BM + GM_BN) * GM_BK * 2;  // 32 KB
-constexpr int GM_SMEM = GM_STAGES * GM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int gm_smem(int stages) { return stages * GM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
 
 struct GemmEpi {
   int M, N, K, mode, splits;
@@ -35,7 +40,8 @@ struct GemmEpi {
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + expf(-1.702f * x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-__global__ void __launch_bounds__(GM_THREADS, 2)
+template <int GM_STAGES>
+__global__ void __launch_bounds__(GM_THREADS, GM_STAGES == 3 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmEpi ep) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -69,13 +75,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   // Set-up above overlaps the tail of the previous kernel when launched with programmatic stream serialization (decode);
   // everything below may read what that kernel wrote.  No-op for ordinary launches.
-  pdl_wait();
-  pdl_launch_dependents();
+  // (the producer thread first requests the W tiles of the first ring stages: weights never depend on the previous kernel)
+  if (!(warp == 0 && lane == 0)) {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer
-      for (int kb = 0; kb < nkb; ++kb) {
+      const int npre = nkb < GM_STAGES ? nkb : GM_STAGES;
+      for (int kb = 0; kb < npre; ++kb) {
+        mbar_arrive_expect_tx(&full_bar[kb], GM_STAGE_BYTES);
+        tma_load_2d(smem + kb * GM_STAGE_BYTES + GM_BM * GM_BK * 2, &tmap_b, &full_bar[kb], (kb0 + kb) * GM_BK, n0);
+      }
+      pdl_wait();
+      pdl_launch_dependents();
+      for (int kb = 0; kb < npre; ++kb) tma_load_2d(smem + kb * GM_STAGE_BYTES, &tmap_a, &full_bar[kb], (kb0 + kb) * GM_BK, m0);
+      for (int kb = npre; kb < nkb; ++kb) {
         const int s = kb % GM_STAGES;
         mbar_wait(&empty_bar[s], ((kb / GM_STAGES) & 1) ^ 1);
         unsigned char* sa = smem + s * GM_STAGE_BYTES;
@@ -191,7 +208,8 @@ static bool gemm_init() {
     return false;
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
+  e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem(3));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem(6));
   if (e != cudaSuccess) {
     g_init_err = "cudaFuncSetAttribute(gemm_tc_kernel) failed";
     g_encode = nullptr;
@@ -242,14 +260,21 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(GM_THREADS);
-  cfg.dynamicSmemBytes = GM_SMEM;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const bool deep = (int)(grid.x * grid.y * grid.z) <= num_sms && !getenv("VDD_GEMM_SHALLOW");  // one wave at one CTA per SM
+  cfg.dynamicSmemBytes = gm_smem(deep ? 6 : 3);
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = a.pdl ? 1 : 0;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, ta, tb, ep);
+  cudaError_t le = deep ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<6>, ta, tb, ep) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<3>, ta, tb, ep);
   if (a.defer_reduce) *a.defer_reduce = ep.splits > 1 ? ep.splits : 0;
   if (le != cudaSuccess || ep.splits == 1 || a.defer_reduce) return le;
   return launch_reduce_splits(a.out_f32, a.split_ws, (int64_t)a.M * a.ldc, ep.splits, stream);
