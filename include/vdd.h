@@ -146,7 +146,8 @@ VDD_API int vdd_last_timings(vdd_engine* e, float* vision_ms, float* prefill_ms,
 
 /* Debug (VDD_TRACE=1): globaltimer stamps [148 CTAs][4 phases][6 events] of the middle layer's fused projection chain. */
 VDD_API int vdd_debug_trace(vdd_engine* e, unsigned long long* out_host, int n);
-/* Enqueue one decode step's projection kernels only (4 per layer + lm_head), for bench.py's roofline leg. */
+/* Enqueue one decode step's projection kernels only (4 projections per layer + lm_head, with the norm passes of the
+ * many-row path), no attention / embedding / sampling: bench.py's roofline leg. */
 VDD_API int vdd_bench_projection_chain(vdd_engine* e, void* stream);
 
 /* Stand-alone kernel entry points used by the unit tests and micro-benchmarks (same kernels the engine runs). */

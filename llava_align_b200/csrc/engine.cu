@@ -1237,7 +1237,6 @@ extern "C" int vdd_last_timings(vdd_engine* e, float* v, float* p, float* d) {
 // the real step: bench.py times this chain with CUDA events to get the GEMV kernel's average launch duration.
 extern "C" int vdd_bench_projection_chain(vdd_engine* e, void* stream_v) {
   if (!e || !e->prefilled) return fail(VDD_ERR_STATE, "vdd_prefill must run first");
-  if (e->R > 8) return fail(VDD_ERR_UNSUPPORTED, "projection chain is the R<=8 GEMV path");
   return decode_step_enqueue(e, nullptr, (cudaStream_t)stream_v, true);
 }
 

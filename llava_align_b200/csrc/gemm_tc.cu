@@ -24,12 +24,18 @@ constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 64;
 //   3 x 32 KB per CTA => two CTAs per SM, one's epilogue overlaps the other's main loop (prefill, ViT: many waves of tiles);
 //   6 x 32 KB, one CTA per SM, for grids that fit the machine in one wave anyway (decode with > 8 rows: 96-128 CTAs, each a
 //   pure weight stream) -- twice the bytes in flight per SM (measured 3.0 TB/s with 3 stages: latency-bound, not HBM-bound).
+//   The deep variant also takes its N-tile width at run time (32..256 weight rows, a multiple of 16), chosen so that the
+//   tiles of a decode projection fill the SMs in ONE even wave: gate_up (22016 rows) as 138 tiles of 160 rows instead of
+//   172 tiles of 128 (which leaves 24 SMs with two tiles and the kernel waiting on them), qkv as 128 tiles of 96.
 constexpr int GM_THREADS = 192;
 constexpr int GM_STAGE_BYTES = (GM_BM + GM_BN) * GM_BK * 2;  // 32 KB
-constexpr int gm_smem(int stages) { return stages * GM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
+constexpr int GM_DEEP_MAX_STAGES = 8, GM_DEEP_TMEM_COLS = 256;
+constexpr int GM_SMEM_MAX = 227 * 1024;
+constexpr int gm_smem(int stages, int stage_bytes = GM_STAGE_BYTES) { return stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/; }
 
 struct GemmEpi {
   int M, N, K, mode, splits;
+  int bn, stages;  // deep variant: N-tile width and ring depth (the shallow variant is compiled for 128 / 3)
   const __nv_bfloat16* bias;
   const int32_t* row_map;
   float* out_f32;
@@ -40,19 +46,23 @@ struct GemmEpi {
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + expf(-1.702f * x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int GM_STAGES>
-__global__ void __launch_bounds__(GM_THREADS, GM_STAGES == 3 ? 2 : 1)
+template <bool DEEP>
+__global__ void __launch_bounds__(GM_THREADS, DEEP ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmEpi ep) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GM_STAGES * GM_STAGE_BYTES);
+  const int GM_STAGES = DEEP ? ep.stages : 3;
+  const int BN = DEEP ? ep.bn : GM_BN;
+  const int STAGE_BYTES = (GM_BM + BN) * GM_BK * 2;
+  constexpr int TMEM_COLS = DEEP ? GM_DEEP_TMEM_COLS : GM_BN;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GM_STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + GM_STAGES;
   uint64_t* tmem_full = empty_bar + GM_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * GM_BN, m0 = blockIdx.y * GM_BM;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM_BM;
   // split-K (skinny decode GEMMs whose N/128 tiles cannot fill 148 SMs): this CTA owns k-blocks [kb0, kb1)
   const int nkb_all = (ep.K + GM_BK - 1) / GM_BK;
   const int kb0 = (int)(((long long)blockIdx.z * nkb_all) / ep.splits), kb1 = (int)(((long long)(blockIdx.z + 1) * nkb_all) / ep.splits);
@@ -68,7 +78,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<GM_BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -86,18 +96,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // ===== TMA producer
       const int npre = nkb < GM_STAGES ? nkb : GM_STAGES;
       for (int kb = 0; kb < npre; ++kb) {
-        mbar_arrive_expect_tx(&full_bar[kb], GM_STAGE_BYTES);
-        tma_load_2d(smem + kb * GM_STAGE_BYTES + GM_BM * GM_BK * 2, &tmap_b, &full_bar[kb], (kb0 + kb) * GM_BK, n0);
+        mbar_arrive_expect_tx(&full_bar[kb], STAGE_BYTES);
+        tma_load_2d(smem + kb * STAGE_BYTES + GM_BM * GM_BK * 2, &tmap_b, &full_bar[kb], (kb0 + kb) * GM_BK, n0);
       }
       pdl_wait();
       pdl_launch_dependents();
-      for (int kb = 0; kb < npre; ++kb) tma_load_2d(smem + kb * GM_STAGE_BYTES, &tmap_a, &full_bar[kb], (kb0 + kb) * GM_BK, m0);
+      for (int kb = 0; kb < npre; ++kb) tma_load_2d(smem + kb * STAGE_BYTES, &tmap_a, &full_bar[kb], (kb0 + kb) * GM_BK, m0);
       for (int kb = npre; kb < nkb; ++kb) {
         const int s = kb % GM_STAGES;
         mbar_wait(&empty_bar[s], ((kb / GM_STAGES) & 1) ^ 1);
-        unsigned char* sa = smem + s * GM_STAGE_BYTES;
+        unsigned char* sa = smem + s * STAGE_BYTES;
         unsigned char* sb = sa + GM_BM * GM_BK * 2;
-        mbar_arrive_expect_tx(&full_bar[s], GM_STAGE_BYTES);
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
         tma_load_2d(sa, &tmap_a, &full_bar[s], (kb0 + kb) * GM_BK, m0);
         tma_load_2d(sb, &tmap_b, &full_bar[s], (kb0 + kb) * GM_BK, n0);
       }
@@ -105,12 +115,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer (single thread)
-      constexpr uint32_t idesc = umma_idesc_bf16(GM_BM, GM_BN);
+      const uint32_t idesc = umma_idesc_bf16(GM_BM, BN);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % GM_STAGES;
         mbar_wait(&full_bar[s], (kb / GM_STAGES) & 1);
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + s * GM_STAGE_BYTES);
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t sb = sa + GM_BM * GM_BK * 2;
         const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
 #pragma unroll
@@ -129,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int64_t orow = -1;
     if (row < ep.M) orow = ep.row_map ? ep.row_map[row] : row;
 #pragma unroll 1
-    for (int c = 0; c < GM_BN / 16; ++c) {
+    for (int c = 0; c < BN / 16; ++c) {
       uint32_t rr[16];
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + c * 16, rr);
       tmem_ld_wait();
@@ -186,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<GM_BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -208,8 +218,8 @@ static bool gemm_init() {
     return false;
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem(3));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem(6));
+  e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem(3));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_MAX);
   if (e != cudaSuccess) {
     g_init_err = "cudaFuncSetAttribute(gemm_tc_kernel) failed";
     g_encode = nullptr;
@@ -219,11 +229,11 @@ static bool gemm_init() {
 }
 const char* gemm_init_error() { return g_init_err; }
 
-// 2D bf16 row-major [rows, K] tensor map with a {64, 128} box and 128-byte swizzle
-static bool make_tmap(CUtensorMap* m, const void* ptr, int rows, int K) {
+// 2D bf16 row-major [rows, K] tensor map with a {64, box_rows} box and 128-byte swizzle
+static bool make_tmap(CUtensorMap* m, const void* ptr, int rows, int K, int box_rows = GM_BM) {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {GM_BK, GM_BM};
+  cuuint32_t box[2] = {GM_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -236,7 +246,6 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0) return cudaSuccess;
   if ((a.K % 8) != 0 || (a.N % 16) != 0 || ((uintptr_t)a.a & 15) || ((uintptr_t)a.w & 15)) return cudaErrorInvalidValue;
   CUtensorMap ta, tb;
-  if (!make_tmap(&ta, a.a, a.M, a.K) || !make_tmap(&tb, a.w, a.N, a.K)) return cudaErrorInvalidValue;
   GemmEpi ep;
   ep.M = a.M; ep.N = a.N; ep.K = a.K; ep.mode = a.epilogue;
   ep.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
@@ -266,15 +275,41 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const bool deep = (int)(grid.x * grid.y * grid.z) <= num_sms && !getenv("VDD_GEMM_SHALLOW");  // one wave at one CTA per SM
-  cfg.dynamicSmemBytes = gm_smem(deep ? 6 : 3);
+  static const bool shallow_only = getenv("VDD_GEMM_SHALLOW") != nullptr, fixed_bn = getenv("VDD_GEMM_BN128") != nullptr;
+  ep.bn = GM_BN;
+  ep.stages = 3;
+  bool deep = false;
+  if (!shallow_only) {
+    if (a.M <= GM_BM && ep.splits == 1 && !fixed_bn) {
+      // decode-sized projection without split-K: widen / narrow the N tile until the tiles form one even wave over the SMs
+      int bn = ((a.N + num_sms - 1) / num_sms + 15) / 16 * 16;
+      if (bn < 32) bn = 32;
+      if (bn <= 256) {
+        ep.bn = bn;
+        grid.x = (a.N + bn - 1) / bn;
+      }
+    }
+    deep = (int)(grid.x * grid.y * grid.z) <= num_sms;  // one wave at one CTA per SM
+  }
+  if (deep) {
+    const int stage_bytes = (GM_BM + ep.bn) * GM_BK * 2;
+    ep.stages = (GM_SMEM_MAX - 1024 - 256) / stage_bytes;
+    if (ep.stages > GM_DEEP_MAX_STAGES) ep.stages = GM_DEEP_MAX_STAGES;
+    cfg.dynamicSmemBytes = gm_smem(ep.stages, stage_bytes);
+  } else {
+    ep.bn = GM_BN;
+    grid.x = (a.N + GM_BN - 1) / GM_BN;
+    cfg.dynamicSmemBytes = gm_smem(3);
+  }
+  cfg.gridDim = grid;
+  if (!make_tmap(&ta, a.a, a.M, a.K) || !make_tmap(&tb, a.w, a.N, a.K, ep.bn)) return cudaErrorInvalidValue;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = a.pdl ? 1 : 0;
-  cudaError_t le = deep ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<6>, ta, tb, ep) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<3>, ta, tb, ep);
+  cudaError_t le = deep ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, ta, tb, ep) : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false>, ta, tb, ep);
   if (a.defer_reduce) *a.defer_reduce = ep.splits > 1 ? ep.splits : 0;
   if (le != cudaSuccess || ep.splits == 1 || a.defer_reduce) return le;
   return launch_reduce_splits(a.out_f32, a.split_ws, (int64_t)a.M * a.ldc, ep.splits, stream);
