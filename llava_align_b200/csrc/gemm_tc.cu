@@ -46,6 +46,52 @@ struct GemmEpi {
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + expf(-1.702f * x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// Fused epilogue of 16 consecutive output columns of one row (shared by all variants of the kernel).
+__device__ __forceinline__ void gm_store16(const GemmEpi& ep, int64_t orow, int col, float (&v)[16], int zplane) {
+  if (ep.bias && zplane == 0) {
+    const uint4 b0 = *reinterpret_cast<const uint4*>(ep.bias + col);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(ep.bias + col + 8);
+    const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[2 * i] += bf16lo(bw[i]); v[2 * i + 1] += bf16hi(bw[i]); }
+  }
+  if (ep.mode == GEMM_OUT_F32 || ep.mode == GEMM_OUT_ADD_F32) {
+    // split-K: slice z writes its partial to scratch plane z; the planes are added in order by a later pass
+    float4* o = reinterpret_cast<float4*>(ep.out_f32 + (ep.splits > 1 ? (int64_t)zplane * ep.M * ep.ldc : 0) + orow * ep.ldc + col);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 t = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if (ep.mode == GEMM_OUT_ADD_F32 && ep.splits == 1) {
+        const float4 old = o[i];
+        t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+      }
+      o[i] = t;
+    }
+  } else if (ep.mode == GEMM_OUT_SWIGLU) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float g0 = v[4 * i], u0 = v[4 * i + 1], g1 = v[4 * i + 2], u1 = v[4 * i + 3];
+      pk[i] = pack_bf16(g0 / (1.0f + expf(-g0)) * u0, g1 / (1.0f + expf(-g1)) * u1);
+    }
+    *reinterpret_cast<uint4*>(ep.out_bf16 + orow * ep.ldc + (col >> 1)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  } else {
+    if (ep.mode == GEMM_OUT_BF16_QGELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = quick_gelu(v[i]);
+    } else if (ep.mode == GEMM_OUT_BF16_GELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+    uint4* o = reinterpret_cast<uint4*>(ep.out_bf16 + orow * ep.ldc + col);
+    o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
 template <bool DEEP>
 __global__ void __launch_bounds__(GM_THREADS, DEEP ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmEpi ep) {
@@ -145,51 +191,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tmem_ld_wait();
       const int col = n0 + c * 16;
       if (orow >= 0 && col < ep.N) {
-      float v[16];
+        float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
-      if (ep.bias && blockIdx.z == 0) {
-        const uint4 b0 = *reinterpret_cast<const uint4*>(ep.bias + col);
-        const uint4 b1 = *reinterpret_cast<const uint4*>(ep.bias + col + 8);
-        const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { v[2 * i] += bf16lo(bw[i]); v[2 * i + 1] += bf16hi(bw[i]); }
-      }
-      if (ep.mode == GEMM_OUT_F32 || ep.mode == GEMM_OUT_ADD_F32) {
-        // split-K: slice z writes its partial to scratch plane z; reduce_splits_kernel adds the planes in order
-        float4* o = reinterpret_cast<float4*>(ep.out_f32 + (ep.splits > 1 ? (int64_t)blockIdx.z * ep.M * ep.ldc : 0) + orow * ep.ldc + col);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 t = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          if (ep.mode == GEMM_OUT_ADD_F32 && ep.splits == 1) {
-            const float4 old = o[i];
-            t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
-          }
-          o[i] = t;
-        }
-      } else if (ep.mode == GEMM_OUT_SWIGLU) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float g0 = v[4 * i], u0 = v[4 * i + 1], g1 = v[4 * i + 2], u1 = v[4 * i + 3];
-          pk[i] = pack_bf16(g0 / (1.0f + expf(-g0)) * u0, g1 / (1.0f + expf(-g1)) * u1);
-        }
-        *reinterpret_cast<uint4*>(ep.out_bf16 + orow * ep.ldc + (col >> 1)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      } else {
-        if (ep.mode == GEMM_OUT_BF16_QGELU) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = quick_gelu(v[i]);
-        } else if (ep.mode == GEMM_OUT_BF16_GELU) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-        }
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-        uint4* o = reinterpret_cast<uint4*>(ep.out_bf16 + orow * ep.ldc + col);
-        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
+        gm_store16(ep, orow, col, v, (int)blockIdx.z);
       }
       __syncwarp();
     }
@@ -197,6 +202,134 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+
+// ------------------------------------------------------------------------------------------------ wide persistent variant
+// Prefill / ViT / projector GEMMs (M > 128 rows): the 128x128 tile above reads 8 KB of shared memory per UMMA of 64 clocks --
+// exactly the 128 B/clk an SM can deliver -- and measured 38-52 % tensor-pipe activity (profiles/r1_ncu_prefill.json).  Here a
+// tile is 128 x 256 (UMMA 128x256x16: 12 KB per 128 clocks = 96 B/clk), CTAs are persistent (one per SM) and walk the tiles
+// m-fastest so the 6 M-tiles of a weight tile hit it in L2, and the fp32 accumulator is double-buffered in TMEM (2 x 256
+// columns) so the four epilogue warps drain tile i while the tensor core works on tile i+1.
+constexpr int GW_BN = 256, GW_STAGES = 4;
+constexpr int GW_STAGE_BYTES = (GM_BM + GW_BN) * GM_BK * 2;  // 48 KB
+constexpr int GW_SMEM = GW_STAGES * GW_STAGE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmEpi ep,
+                    int m_tiles, int n_tiles) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GW_STAGES * GW_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + GW_STAGES;
+  uint64_t* tfull_bar = empty_bar + GW_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (ep.K + GM_BK - 1) / GM_BK;
+  const int tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < GW_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int gi = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * GM_BM, n0 = (tile / m_tiles) * GW_BN;
+        for (int kb = 0; kb < nkb; ++kb, ++gi) {
+          const int s = gi % GW_STAGES;
+          mbar_wait(&empty_bar[s], ((gi / GW_STAGES) & 1) ^ 1);
+          unsigned char* sa = smem + s * GW_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], GW_STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, &full_bar[s], kb * GM_BK, m0);
+          tma_load_2d(sa + GM_BM * GM_BK * 2, &tmap_b, &full_bar[s], kb * GM_BK, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GM_BM, GW_BN);
+      int gi = 0, it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)buf * GW_BN;
+        for (int kb = 0; kb < nkb; ++kb, ++gi) {
+          const int s = gi % GW_STAGES;
+          mbar_wait(&full_bar[s], (gi / GW_STAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * GW_STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + GM_BM * GM_BK * 2);
+#pragma unroll
+          for (int k = 0; k < GM_BK / 16; ++k) umma_bf16(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile % m_tiles) * GM_BM, n0 = (tile / m_tiles) * GW_BN;
+      const int buf = it & 1;
+      const int row = m0 + quad * 32 + lane;
+      int64_t orow = -1;
+      if (row < ep.M) orow = ep.row_map ? ep.row_map[row] : row;
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < GW_BN / 16; c += 2) {  // two 16-column chunks per TMEM round trip
+        uint32_t r0[16], r1[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * GW_BN + c * 16;
+        tmem_ld16(ta, r0);
+        tmem_ld16(ta + 16, r1);
+        tmem_ld_wait();
+        const int col = n0 + c * 16;
+        if (orow >= 0 && col < ep.N) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
+          gm_store16(ep, orow, col, v, 0);
+        }
+        if (orow >= 0 && col + 16 < ep.N) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
+          gm_store16(ep, orow, col + 16, v, 0);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -220,6 +353,7 @@ static bool gemm_init() {
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem(3));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_MAX);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GW_SMEM);
   if (e != cudaSuccess) {
     g_init_err = "cudaFuncSetAttribute(gemm_tc_kernel) failed";
     g_encode = nullptr;
@@ -275,7 +409,28 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  static const bool shallow_only = getenv("VDD_GEMM_SHALLOW") != nullptr, fixed_bn = getenv("VDD_GEMM_BN128") != nullptr;
+  static const bool shallow_only = getenv("VDD_GEMM_SHALLOW") != nullptr, fixed_bn = getenv("VDD_GEMM_BN128") != nullptr,
+                    no_wide = getenv("VDD_GEMM_NARROW") != nullptr;
+  const int wide_tiles = ((a.M + GM_BM - 1) / GM_BM) * ((a.N + GW_BN - 1) / GW_BN);
+  if (a.M > GM_BM && ep.splits == 1 && !no_wide && !shallow_only && 2 * wide_tiles >= num_sms) {
+    // GEMM-shaped work (prefill of all streams, ViT, projector): persistent 128x256 tiles, TMEM double buffer.  Problems with
+    // fewer than ~half a wave of such tiles (single-image ViT projections: 20 tiles) keep the 128x128 tiles below.
+    const int m_tiles = (a.M + GM_BM - 1) / GM_BM, n_tiles = (a.N + GW_BN - 1) / GW_BN;
+    ep.bn = GW_BN;
+    ep.stages = GW_STAGES;
+    if (!make_tmap(&ta, a.a, a.M, a.K) || !make_tmap(&tb, a.w, a.N, a.K, GW_BN)) return cudaErrorInvalidValue;
+    const int tiles = m_tiles * n_tiles;
+    cfg.gridDim = dim3(tiles < num_sms ? tiles : num_sms);
+    cfg.dynamicSmemBytes = GW_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute atw[1];
+    atw[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    atw[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = atw;
+    cfg.numAttrs = a.pdl ? 1 : 0;
+    if (a.defer_reduce) *a.defer_reduce = 0;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_wide_kernel, ta, tb, ep, m_tiles, n_tiles);
+  }
   ep.bn = GM_BN;
   ep.stages = 3;
   bool deep = false;
