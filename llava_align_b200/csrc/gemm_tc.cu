@@ -412,9 +412,10 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   static const bool shallow_only = getenv("VDD_GEMM_SHALLOW") != nullptr, fixed_bn = getenv("VDD_GEMM_BN128") != nullptr,
                     no_wide = getenv("VDD_GEMM_NARROW") != nullptr;
   const int wide_tiles = ((a.M + GM_BM - 1) / GM_BM) * ((a.N + GW_BN - 1) / GW_BN);
-  if (a.M > GM_BM && ep.splits == 1 && !no_wide && !shallow_only && 2 * wide_tiles >= num_sms) {
+  if (a.M > GM_BM && ep.splits == 1 && !no_wide && !shallow_only && wide_tiles >= num_sms) {
     // GEMM-shaped work (prefill of all streams, ViT, projector): persistent 128x256 tiles, TMEM double buffer.  Problems with
-    // fewer than ~half a wave of such tiles (single-image ViT projections: 20 tiles) keep the 128x128 tiles below.
+    // less than one wave of such tiles keep the 128x128 tiles below (measured at 670 rows: o_proj / down_proj = 96 wide tiles
+    // 49.6 / 91.2 us against 42.3 / 83.6 us; qkv / gate_up = 288 / 516 tiles 66 / 116 us against 83 / 159 us).
     const int m_tiles = (a.M + GM_BM - 1) / GM_BM, n_tiles = (a.N + GW_BN - 1) / GW_BN;
     ep.bn = GW_BN;
     ep.stages = GW_STAGES;
