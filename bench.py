@@ -141,7 +141,13 @@ def run_reference(a):
 
 
 def workload_config(a, cfg, n, mode="dp"):
-    return {"workload": f"BASELINE.json configs[1]: {cfg.name} bf16 random-init, batch {a.batch}, 1 synthetic "
+    if a.batch == 1 and a.prompt_len == 32 and a.new_tokens == 256:
+        which = "BASELINE.json configs[1]"
+    elif a.batch == 32:
+        which = "BASELINE.json configs[2] shape (POPE-like batch of 32)"
+    else:
+        which = "custom shape (not a BASELINE.json config)"
+    return {"workload": f"{which}: {cfg.name} bf16 random-init, batch {a.batch}, 1 synthetic "
                         f"{cfg.image_size}px image, {a.prompt_len}-token prompt, {a.new_tokens} new tokens, use_dd+use_dd_unk "
                         f"(3 fused streams), cd_alpha=1 cd_beta=0.1, temperature-1 sampling, EOS disabled",
             "global_batch": a.batch, "new_tokens": a.new_tokens, "prompt_len": a.prompt_len, "streams": 3,

@@ -147,7 +147,10 @@ def test_gemv_rmsnorm_swiglu(R):
 
 # ------------------------------------------------------------------------------------------------ tcgen05 GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (670, 768, 256), (300, 384, 1376), (1154, 1024, 640), (96, 4096, 4096),
-                                   (5, 512, 128)])
+                                   (5, 512, 128),
+                                   # at least one wave of 128x256 tiles -> the persistent wide variant (TMEM double buffer),
+                                   # incl. N off the 256 tile and several tiles per CTA
+                                   (1300, 4096, 512), (2000, 3088, 320), (670, 12288, 4096)])
 def test_gemm_epilogues(M, N, K):
     L = _lib()
     lib = L.load()
