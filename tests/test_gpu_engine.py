@@ -171,9 +171,11 @@ def test_first_step_attention_matches_reference(engine_model, case):
 
 @pytest.mark.parametrize("B,use_unk,use_none,with_image,T", [(2, True, True, True, 10), (3, True, True, True, 9),
                                                             (4, True, False, True, 7), (1, False, False, False, 5),
-                                                            (2, True, False, False, 6), (5, True, True, True, 4)])
+                                                            (2, True, False, False, 6), (5, True, True, True, 4),
+                                                            (50, True, True, True, 5)])
 def test_row_shapes_against_oracle(engine_model, B, use_unk, use_none, with_image, T):
-    """Row counts on both sides of the GEMV / tensor-core decode switch (R = 6, 9, 8, 1, 4, 15), text-only prompts, and the
+    """Row counts on both sides of the GEMV / tensor-core decode switch (R = 6, 9, 8, 1, 4, 15) and beyond one 128-row tile
+    (R = 150: no split-K planes, two M tiles), text-only prompts, and the
     row-wise definition of the use_dd stream for B > 1, teacher-forced on the oracle's tokens."""
     cfg, m, oracle = engine_model
     ids, img = make_inputs(cfg, B, T, 200 + B + T)
