@@ -79,3 +79,30 @@ def test_generate_kwarg_surface():
     assert vdd_sampler_installed()
     from vcd_utils.vcd_sample import evolve_vcd_sampling as e2  # the reference's import path
     assert e2 is evolve_vcd_sampling
+
+
+def test_null_arguments_return_error_codes_not_crashes():
+    """Error behaviour of the C ABI (include/vdd.h: 0 on success, negative code + vdd_last_error() otherwise), exercised on
+    the argument checks that run before any CUDA call."""
+    from llava_align_b200 import _lib
+    lib = _lib.load()
+    assert lib.vdd_set_attention_capture(None, None, 0) < 0 and lib.vdd_last_error()
+    assert lib.vdd_decode_step(None, None, None) < 0
+    assert lib.vdd_prefill(None, None, 1, 1, 1, 0, 0, 1, None) < 0
+    assert lib.vdd_bench_projection_chain(None, None) < 0
+    assert lib.vdd_load_tensor(None, b"x", None, None, 0, None) < 0
+    assert lib.vdd_num_streams(None) == 0 and lib.vdd_logits(None) is None
+    assert lib.vdd_launch_count(None, 0) == 0
+    assert lib.vdd_skinny_gemm_trace(None) == 0  # disarming the debug trace is always legal
+
+
+def test_attentions_tuple_serves_only_what_is_materialised():
+    """`attentions[0][-1]` is the one entry the reference's drivers read (llava_calibrate.py:180); anything else must raise
+    rather than return something made up."""
+    from llava_align_b200.model import _StepAttentions
+    m = torch.zeros(1, 2, 5, 5)
+    a0, a1 = _StepAttentions(0, 4, m), _StepAttentions(1, 4, None)
+    assert len(a0) == 4 and a0[-1] is m and a0[3] is m
+    for bad in (lambda: a0[0], lambda: a0[2], lambda: a1[-1], lambda: list(a0)):
+        with pytest.raises(NotImplementedError):
+            bad()
