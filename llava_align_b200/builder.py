@@ -55,14 +55,27 @@ def load_pretrained_model(model_path, model_base=None, model_name=None, load_8bi
         for name, t in iter_checkpoint_tensors(model_path, vision_tower_path):
             model.engine.load_tensor(name, t)
         model.engine.check_complete()
+        import logging
+        from .checkpoint import find_vision_tower_dir, _read_json
+        hf_cfg = _read_json(os.path.join(model_path, "config.json"))
+        # reference builder.py:143-146: context_len = config.max_sequence_length if the checkpoint defines it, else 2048
+        # (released LLaVA-1.5 configs do not define it)
+        if "max_sequence_length" in hf_cfg:
+            model.config.max_sequence_length = int(hf_cfg["max_sequence_length"])
+        # from_pretrained also reads generation_config.json into model.generation_config (defaults of generate())
+        gpath = os.path.join(model_path, "generation_config.json")
+        if os.path.exists(gpath):
+            for k, v in _read_json(gpath).items():
+                if hasattr(model.generation_config, k):
+                    setattr(model.generation_config, k, v)
         try:
             from transformers import AutoTokenizer, CLIPImageProcessor
-            from .checkpoint import find_vision_tower_dir, _read_json
             tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)
-            vdir = find_vision_tower_dir(model_path, _read_json(os.path.join(model_path, "config.json")), vision_tower_path)
+            vdir = find_vision_tower_dir(model_path, hf_cfg, vision_tower_path)
             image_processor = CLIPImageProcessor.from_pretrained(vdir or model_path)
             model.get_vision_tower().image_processor = image_processor
-        except Exception:
-            pass  # weights-only directories (tests) carry no tokenizer / preprocessor files
-    context_len = getattr(model.config, "max_sequence_length", 2048)  # builder.py:143-146
+        except (FileNotFoundError, OSError, ValueError) as ex:
+            # weights-only directories (tests) carry no tokenizer / preprocessor files; anything else propagates
+            logging.getLogger(__name__).warning("no tokenizer / image processor under %s (%s): returning None for them",
+                                                model_path, type(ex).__name__)
     return tokenizer, model, image_processor, context_len

@@ -76,6 +76,12 @@ def tiny_config(**kw) -> VddConfig:
 
 
 def by_name(name: str) -> VddConfig:
+    """'llava-v1.5-7b', 'llava-v1.5-13b', 'tiny'; a suffix '@N' keeps the real widths but only N decoder layers
+    (layer-reduced real-width models for parity tests against the CPU oracle)."""
+    if "@" in name:
+        from dataclasses import replace
+        base, n_layers = name.rsplit("@", 1)
+        return replace(by_name(base), num_hidden_layers=int(n_layers), name=name)
     n = name.lower()
     if "13b" in n:
         return LLAVA_15_13B

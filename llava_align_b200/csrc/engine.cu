@@ -1145,6 +1145,10 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
     mix((uint64_t)(uintptr_t)e->kv.p); mix((uint64_t)(uintptr_t)e->logits.p); mix((uint64_t)e->kv_layer_stride);
     mix((uint64_t)(uintptr_t)e->meta.p); mix((uint64_t)(uintptr_t)e->dec_f32.p); mix((uint64_t)(uintptr_t)e->dec_bf16.p);
     mix((uint64_t)(uintptr_t)e->sk_ws.p); mix((uint64_t)(uintptr_t)e->split_ws.p);
+    // the meta carve-out places the sampler arguments, barriers and work table BEHIND the [B, max_new] sequence buffer, so
+    // their addresses move with max_new even when every shape above is unchanged
+    mix((uint64_t)e->max_new); mix((uint64_t)(uintptr_t)e->d_sargs); mix((uint64_t)(uintptr_t)e->d_bar);
+    mix((uint64_t)(uintptr_t)e->d_item_row); mix((uint64_t)(uintptr_t)e->d_seq_out);
     int per_step_launches = 0;
     const bool graph = e->use_graph && st != nullptr;  // the legacy default stream cannot be captured
     if (graph && (!e->graph_exec || e->graph_key != key)) {

@@ -159,6 +159,17 @@ class VddEngine:
         blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
         _lib.check(self.lib.vdd_tp_comm_open(self.h, C.create_string_buffer(blob, len(blob))), "vdd_tp_comm_open")
         dist.barrier()
+        self._dist = dist
+
+    def tp_broadcast(self, t: torch.Tensor) -> torch.Tensor:
+        """Make a per-rank tensor (the sampler's Exp(1) variates) identical on every tensor-parallel rank: every rank samples
+        the same token from the same all-gathered logits only if it races against the same variates, and ranks that pick
+        different tokens would silently diverge in their sharded KV caches."""
+        if self.tp_size > 1:
+            if getattr(self, "_dist", None) is None:
+                raise _lib.VddError("tensor-parallel engine without tp_setup(): cannot synchronise the sampler's variates")
+            self._dist.broadcast(t, 0)
+        return t
 
     @staticmethod
     def tp_unique_id() -> bytes:
@@ -202,6 +213,15 @@ class VddEngine:
         last layer of the main stream (vdd_set_attention_capture)."""
         ids = input_ids.detach().to("cpu", torch.int64).contiguous()
         B, T = ids.shape
+        # the library copies B*3*S*S elements from the raw pointer: refuse anything else (the reference also accepts lists and
+        # 5-D multi-crop tensors, llava_arch.py:97 -- outside the one-image-per-row path)
+        for what, t in (("images", images), ("images_cd", images_cd)):
+            if t is None:
+                continue
+            S = self.cfg.image_size
+            if not isinstance(t, torch.Tensor) or tuple(t.shape) != (B, 3, S, S):
+                got = tuple(t.shape) if isinstance(t, torch.Tensor) else type(t).__name__
+                raise ValueError(f"{what} must be a tensor of shape {(B, 3, S, S)} (one {S}px image per prompt row), got {got}")
         if attention_out is not None:
             _lib.check(self.lib.vdd_set_attention_capture(self.h, C.c_void_p(attention_out.data_ptr()), attention_out.numel()),
                        "vdd_set_attention_capture")

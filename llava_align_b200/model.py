@@ -87,7 +87,9 @@ class LlavaLlamaForCausalLM:
         self.config = SimpleNamespace(mm_use_im_start_end=False, mm_use_im_patch_token=False, vocab_size=cfg.vocab_size,
                                       hidden_size=cfg.hidden_size, pad_token_id=cfg.pad_token_id,
                                       eos_token_id=cfg.eos_token_id, bos_token_id=cfg.bos_token_id,
-                                      max_sequence_length=cfg.max_position_embeddings, is_encoder_decoder=False)
+                                      max_position_embeddings=cfg.max_position_embeddings, is_encoder_decoder=False)
+        # no `max_sequence_length`: LLaVA-1.5 configs do not define it, so the reference's loader reports context_len 2048
+        # (builder.py:143-146); the checkpoint loader sets it when a config.json does
         # HF GenerationConfig defaults (temperature 1.0, top_k 50, top_p 1.0)
         self.generation_config = SimpleNamespace(temperature=1.0, top_k=50, top_p=1.0, do_sample=False, max_new_tokens=None,
                                                  max_length=20, eos_token_id=cfg.eos_token_id, pad_token_id=cfg.pad_token_id,
@@ -135,6 +137,10 @@ class LlavaLlamaForCausalLM:
             raise NotImplementedError("custom stopping_criteria are not supported: EOS and max_new_tokens stop generation")
         if input_ids.dim() == 1:
             input_ids = input_ids.unsqueeze(0)
+        if attention_mask is not None and not bool(torch.as_tensor(attention_mask).bool().all()):
+            # the reference rebuilds the decode-step mask as all ones (llava_arch.py:91-94): padded
+            # batches are not a supported input there either; refuse instead of attending to pad tokens
+            raise NotImplementedError("padded prompts (attention_mask with zeros) are not supported: pass equal-length rows")
         B, T = input_ids.shape
         if max_new_tokens is None:
             max_new_tokens = gc.max_new_tokens
@@ -175,6 +181,7 @@ class LlavaLlamaForCausalLM:
         if do_sample and params.top_k != 1:
             # torch.multinomial(probs, 1) == argmax(probs / Exp(1)); the variates come from torch's CUDA generator
             q = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device).exponential_(1)
+            q = self.engine.tp_broadcast(q)  # tensor parallel: every rank must race against rank 0's variates
         want_scores = bool(opt["output_scores"] and opt["return_dict_in_generate"])
         scores_buf = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device) if want_scores else None
         attn_buf = None

@@ -90,7 +90,7 @@ def test_load_pretrained_model_from_directory_matches_state_dict(tmp_path):
     llava, _ = write_checkpoint(str(tmp_path), cfg, sd)
     evolve_vcd_sampling()
     tok, m, proc, ctx = load_pretrained_model(llava, None, "llava-tiny")
-    assert tok is None and proc is None and ctx == cfg.max_position_embeddings
+    assert tok is None and proc is None and ctx == 2048  # reference builder.py:143-146: no max_sequence_length in the config
     ref = LlavaLlamaForCausalLM(cfg, "cuda:0")
     ref.load_state_dict(sd)
     ids, img = make_inputs(cfg, 2, 12, 31)

@@ -87,25 +87,32 @@ def test_generate_matches_reference_golden(engine_model, case):
     toks, steps = m.engine.generate(ids, img, bool(f.get("use_dd_unk")), bool(f.get("use_dd")), params, n, q, scores, img_cd)
     assert steps == ref_seq.shape[1] - case["T"]
     got_scores = scores[:steps].cpu()
-    # step 0 is free of feedback: sets and values must agree within the logit tolerance
-    fin0 = torch.isfinite(ref_scores[0])
-    mism = (torch.isfinite(got_scores[0]) != fin0)
-    assert mism.sum().item() <= 2, mism.sum()   # a token sitting within bf16 noise of the cutoff may flip
-    both = fin0 & torch.isfinite(got_scores[0])
     a = 1.0 + (0.5 if f.get("cd_alpha") is None else f["cd_alpha"])
     tol = LOGIT_TOL * (2 * a) / (s.get("temperature") or 1.0)
-    assert (got_scores[0][both] - ref_scores[0][both]).abs().max().item() <= tol
-    if greedy:
-        # token-exact on the greedy path unless the reference's own top-2 margin is inside the tolerance
-        new_ref = ref_seq[:, case["T"]:]
-        for st in range(steps):
-            if torch.equal(toks[:, st], new_ref[:, st]):
-                continue
-            top2 = torch.topk(ref_scores[st], 2, dim=-1).values
-            margin = (top2[:, 0] - top2[:, 1]).min().item()
-            assert margin <= tol, (st, margin, toks[:, st], new_ref[:, st])
-            break
-    assert torch.equal(toks[:, :0].cpu(), ref_seq[:, case["T"]:case["T"]])
+    new_ref = ref_seq[:, case["T"]:]
+    toks = toks.cpu()
+    compared = 0
+    for st in range(steps):
+        # While both sides have emitted the same tokens they are in the same state: the post-warper scores of this step
+        # (vcd_sample.py:200) must agree -- same finite set up to tokens sitting within bf16 noise of the cutoff / nucleus
+        # edge, same values within the logit tolerance -- and so must the token drawn with the SAME variates q.
+        fin = torch.isfinite(ref_scores[st])
+        gfin = torch.isfinite(got_scores[st])
+        assert (gfin != fin).sum().item() <= 2 * B, (st, (gfin != fin).sum())
+        both = fin & gfin
+        err = (got_scores[st][both] - ref_scores[st][both]).abs().max().item()
+        assert err <= tol, (st, err)
+        compared += 1
+        if torch.equal(toks[:, st], new_ref[:, st]):
+            continue
+        # a different token is only legitimate at a near-tie of the reference's own decision: greedy = top-2 margin of the
+        # scores; sampled = top-2 margin of the exponential race  score - log q  (argmax(softmax(s)/q) == argmax(s - log q))
+        race = ref_scores[st] if q is None else ref_scores[st] - torch.log(q[st].cpu())
+        top2 = torch.topk(race, 2, dim=-1).values
+        margin = (top2[:, 0] - top2[:, 1]).min().item()
+        assert margin <= tol, (st, margin, toks[:, st], new_ref[:, st])
+        break  # the sequences have legitimately diverged: later steps are no longer comparable
+    assert compared >= 1
 
 
 def test_generate_surface(engine_model):

@@ -19,7 +19,7 @@ def model7b():
     from llava_align_b200.model import evolve_vcd_sampling
     evolve_vcd_sampling()
     _, m, _, ctx = load_pretrained_model("random:llava-v1.5-7b:0", None, "llava-v1.5-7b")
-    assert ctx == 4096
+    assert ctx == 2048  # reference builder.py:143-146
     return m
 
 
