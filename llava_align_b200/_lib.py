@@ -38,6 +38,8 @@ SIGNATURES = {
     "vdd_version": (C.c_int, []),
     "vdd_logit_combine_sample": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int64, C.POINTER(vdd_sample_params), _P, _P,
                                            _P, _P, _P]),
+    "vdd_bench_combine": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int64, C.POINTER(vdd_sample_params), _P, _P, C.c_int,
+                                    C.POINTER(C.c_float), _P]),
     "vdd_create": (C.c_int, [C.POINTER(vdd_config), C.POINTER(_P)]),
     "vdd_destroy": (None, [_P]),
     "vdd_load_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, _P]),

@@ -1032,6 +1032,52 @@ extern "C" int vdd_logit_combine_sample(const float* l, const float* u, const fl
   return VDD_OK;
 }
 
+// K8 alone, `reps` launches captured in ONE CUDA graph and replayed: the per-launch time is the kernel's, not the host's
+// (bench.py's logit-combine GB/s; at B <= 64 a Python-driven loop measures ctypes + allocator overhead instead).
+extern "C" int vdd_bench_combine(const float* l, const float* u, const float* d, int B, int V, int64_t ld, const vdd_sample_params* p,
+                                 const float* q, int64_t* tokens_out, int reps, float* ms_out, void* stream_v) {
+  if (!l || !p || !ms_out || !tokens_out || B <= 0 || V <= 0 || reps < 1) return fail(VDD_ERR_ARG, "bad argument");
+  if (V > 32768) return fail(VDD_ERR_UNSUPPORTED, "vocab %d > 32768", V);
+  cudaStream_t st = (cudaStream_t)stream_v;
+  if (!st) return fail(VDD_ERR_ARG, "graph capture needs a non-default stream");
+  SampleArgs a{};
+  a.l = l; a.u = u; a.d = d; a.q = q; a.tokens_out = tokens_out; a.ld = ld; a.B = B; a.V = V;
+  fill_sample_args(a, *p);
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t ge = nullptr;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  cudaError_t ce = cudaSuccess;
+  for (int i = 0; i < reps && ce == cudaSuccess; ++i) ce = launch_combine_sample(a, nullptr, B, V, st);
+  cudaError_t ee = cudaStreamEndCapture(st, &g);
+  if (ce != cudaSuccess || ee != cudaSuccess) {
+    if (g) cudaGraphDestroy(g);
+    return fail(VDD_ERR_CUDA, "combine graph capture: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+  }
+  ce = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int it = 0; it < 4; ++it) {  // first replay warms up; keep the best of the rest
+    cudaEventRecord(e0, st);
+    cudaGraphLaunch(ge, st);
+    cudaEventRecord(e1, st);
+    cudaStreamSynchronize(st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (it > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaGraphExecDestroy(ge);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "combine graph replay: %s", cudaGetErrorString(ce));
+  *ms_out = best / (float)reps;
+  return VDD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ generate
 static int upload_and_encode(vdd_engine* e, const void* pixels, int B, int slot, cudaStream_t st) {
   const vdd_config& c = e->c;
