@@ -78,4 +78,5 @@ def load_pretrained_model(model_path, model_base=None, model_name=None, load_8bi
             # weights-only directories (tests) carry no tokenizer / preprocessor files; anything else propagates
             logging.getLogger(__name__).warning("no tokenizer / image processor under %s (%s): returning None for them",
                                                 model_path, type(ex).__name__)
+    context_len = getattr(model.config, "max_sequence_length", 2048)  # reference builder.py:143-146
     return tokenizer, model, image_processor, context_len
