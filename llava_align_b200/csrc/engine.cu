@@ -134,6 +134,11 @@ struct vdd_engine {
   // decode buffers (views into dec_f32 / dec_bf16)
   float *resid_d = nullptr, *qkv_d = nullptr, *part_o = nullptr, *part_ml = nullptr, *tp_part = nullptr;
   void *attn_d = nullptr, *h_d = nullptr, *xn_d = nullptr;
+  // whole-step persistent kernel (decode_step.cu): device table of phases for the current plan
+  bool use_step = true, step_ready = false;
+  int step_R = 0;
+  DevBuf step_tab;
+  StepLaunch step_launch{};
   // graph cache
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_key = 0;
@@ -215,7 +220,11 @@ extern "C" int vdd_create(const vdd_config* cfg, vdd_engine** out) {
   // the shared-tile fix-up cost ~14 us against a 15 us stream: profiles/r1_trace_skinny.json); opt-in until chained.
   e->use_skinny = getenv("VDD_SKINNY") != nullptr;
   e->use_fused = getenv("VDD_NO_FUSED") == nullptr;
-  if (getenv("VDD_TRACE")) cudaMalloc(&e->d_trace, (size_t)256 * 4 * 8 * 8);
+  e->use_step = getenv("VDD_NO_STEP") == nullptr;  // VDD_NO_STEP=1: one gemv_kernel chain + one attention launch per layer (round 1)
+  if (getenv("VDD_TRACE")) {
+    cudaMalloc(&e->d_trace, (size_t)256 * 64 * 8 * 8);
+    cudaMemset(e->d_trace, 0, (size_t)256 * 64 * 8 * 8);
+  }
 
   const int64_t H = c.hidden_size, VH = c.v_hidden, VI = c.v_intermediate;
   std::vector<std::pair<std::string, size_t>> order;
@@ -329,7 +338,8 @@ extern "C" void vdd_destroy(vdd_engine* e) {
   cudaDeviceSynchronize();
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   DevBuf* bufs[] = {&e->resid, &e->xn, &e->qkv, &e->qb, &e->attn, &e->hbuf, &e->meta, &e->kv, &e->logits, &e->logits_tp,
-                    &e->dec_f32, &e->dec_bf16, &e->part, &e->img_feats, &e->vis, &e->pix, &e->misc, &e->tp_tmp, &e->split_ws, &e->sk_ws, &e->sk_cnt};
+                    &e->dec_f32, &e->dec_bf16, &e->part, &e->img_feats, &e->vis, &e->pix, &e->misc, &e->tp_tmp, &e->split_ws, &e->sk_ws, &e->sk_cnt,
+                    &e->step_tab};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (e->arena) cudaFree(e->arena);
@@ -576,6 +586,7 @@ extern "C" const float* vdd_image_features(vdd_engine* e) { return e ? (const fl
 
 // ------------------------------------------------------------------------------------------------ prefill
 static int tp_gather_logits(vdd_engine* e, cudaStream_t st);
+static int prepare_step(vdd_engine* e, cudaStream_t st);
 
 static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int with_images, int use_unk, int use_none, int use_cd,
                         int max_new, void* stream_v);
@@ -802,6 +813,7 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   if (c.tp_size > 1) RC(tp_gather_logits(e, st));
   e->logits_cur = (float*)e->logits.p;
   e->prefilled = true;
+  RC(prepare_step(e, st));
   if (e->attn_capture) {
     // the roped queries of the LAST layer are still in qb and its keys are in the cache: materialise the main stream's map
     float* out = e->attn_capture;
@@ -850,6 +862,57 @@ static GemvArgs gv_args(const void* w, const void* x_bf16, const float* x_resid,
   return g;
 }
 
+// Phase table of the whole-step kernel for the CURRENT plan (R rows): qkv_0 | per layer: attention, o, gate_up, down, next qkv /
+// lm_head.  Built outside graph capture (prefill; again when the VCD contrast rows are dropped after step 0).
+static int prepare_step(vdd_engine* e, cudaStream_t st) {
+  e->step_ready = false;
+  const vdd_config& c = e->c;
+  const int H = c.hidden_size, L = c.num_layers, Hl = e->Hl, Il = e->Il, R = e->R;
+  const bool tp = c.tp_size > 1;
+  const bool tpf = tp && e->tp_fused_ready;
+  if (!e->use_step || !e->use_fused || R > 4 || (tp && !tpf)) return VDD_OK;
+  __nv_bfloat16* kbase = (__nv_bfloat16*)e->kv.p;
+  float* lg = tp ? (float*)e->logits_tp.p : (float*)e->logits.p;
+  std::vector<StepPhase> ph;
+  auto gemv = [&](const GemvArgs& g) { StepPhase p{}; p.kind = STEP_GEMV; p.g = g; ph.push_back(p); };
+  auto qkv = [&](int l) {
+    return gv_args(e->lw[l].wqkv, nullptr, e->resid_d, e->lw[l].ln1, c.rms_eps, R, 3 * Hl, H, GEMV_OUT_F32, e->qkv_d, nullptr, 3 * Hl);
+  };
+  const int res_epi = tpf ? GEMV_OUT_TP_PARTIAL : GEMV_OUT_ADD_RESID;
+  gemv(qkv(0));
+  for (int l = 0; l < L; ++l) {
+    const LayerW& w = e->lw[l];
+    StepPhase a{};
+    a.kind = STEP_ATTN;
+    a.kcache = kbase + (size_t)l * e->kv_layer_stride;
+    a.vcache = kbase + (size_t)(L + l) * e->kv_layer_stride;
+    ph.push_back(a);
+    GemvArgs o = gv_args(w.wo, e->attn_d, nullptr, nullptr, 0.f, R, H, Hl, res_epi, e->resid_d, nullptr, H);
+    GemvArgs gu = gv_args(w.wgu, nullptr, e->resid_d, w.ln2, c.rms_eps, R, 2 * Il, H, GEMV_OUT_SWIGLU_BF16, nullptr, e->h_d, Il);
+    GemvArgs dn = gv_args(w.wdown, e->h_d, nullptr, nullptr, 0.f, R, H, Il, res_epi, e->resid_d, nullptr, H);
+    if (tpf) {
+      o.tp_slot = 0; o.tp_counter = 2 * l;
+      dn.tp_slot = 1; dn.tp_counter = 2 * l + 1;
+    }
+    gemv(o); gemv(gu); gemv(dn);
+    if (l + 1 < L) {
+      gemv(qkv(l + 1));
+    } else {
+      GemvArgs hd = gv_args(e->lm_head, nullptr, e->resid_d, e->final_norm, c.rms_eps, R, e->Vl, H, GEMV_OUT_F32, lg, nullptr, e->Vl);
+      if (tpf) { hd.epilogue = GEMV_OUT_TP_LOGITS; hd.tp_counter = 2 * L; }
+      gemv(hd);
+    }
+  }
+  if (!step_kernel_supports(ph.data(), (int)ph.size(), R)) return VDD_OK;  // odd shapes keep the per-layer launches
+  if (plan_decode_step(ph.data(), (int)ph.size(), R, e->num_sms, &e->step_launch) != cudaSuccess) return VDD_OK;
+  RC(ensure(e, e->step_tab, ph.size() * sizeof(StepPhase)));
+  CK(cudaMemcpyAsync(e->step_tab.p, ph.data(), ph.size() * sizeof(StepPhase), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // the host vector goes out of scope
+  e->step_R = R;
+  e->step_ready = true;
+  return VDD_OK;
+}
+
 static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_t st, bool projections_only = false) {
   const vdd_config& c = e->c;
   const int H = c.hidden_size, L = c.num_layers, Hl = e->Hl, Il = e->Il, R = e->R;
@@ -868,6 +931,27 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     return g;
   };
   if (fused) CK(cudaMemsetAsync(e->d_bar, 0, (size_t)(L + 2) * 4 * 4, st));
+  if (fused && e->step_ready && e->step_R == R) {
+    // ONE persistent launch for the whole step (decode_step.cu): weights streamed by a producer warp across all phases
+    if (!projections_only) LK(e, launch_decode_embed(e->embed, tokens, e->resid_d, e->B, e->S, H, st));
+    StepArgs sa{};
+    sa.phases = (const StepPhase*)e->step_tab.p;
+    sa.nph = 1 + 5 * L;
+    sa.skip_attn = projections_only ? 1 : 0;
+    sa.attn.qkv = e->qkv_d; sa.attn.kv_off = e->d_kv_off; sa.attn.kv_cap = e->d_kv_cap; sa.attn.pos = e->d_pos;
+    sa.attn.rope_cos = e->rope_cos; sa.attn.rope_sin = e->rope_sin; sa.attn.out_bf16 = e->attn_d; sa.attn.part_o = e->part_o;
+    sa.attn.part_ml = e->part_ml; sa.attn.counters = e->d_counters; sa.attn.heads = e->heads_l; sa.attn.max_splits = e->max_splits;
+    sa.attn.scale = 0.08838834764831845f;
+    sa.barrier = e->d_bar;
+    if (tpf) sa.tpc = e->tpc;
+    sa.trace = e->d_trace;
+    cudaError_t ce = launch_decode_step(sa, e->step_launch, R, pdl, st);
+    e->launches++;
+    if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "decode step kernel (R=%d, grid %d, %d+1 warps, ring depth %d, %zu B smem): %s", R,
+                                       e->step_launch.grid, e->step_launch.nw, e->step_launch.depth, e->step_launch.smem, cudaGetErrorString(ce));
+    if (!projections_only) e->logits_cur = tpf ? (float*)((char*)e->comm_buf + e->tpc.off_logits) : (float*)e->logits.p;
+    return VDD_OK;
+  }
   // 8 < R <= 256 on one GPU: stream-K tcgen05 chain, one launch per layer (decode_gemm.cu), RMSNorm folded into the epilogues
   const bool skinny = R > 8 && R <= 256 && e->use_skinny && e->sk_counters && !tp;
   if (skinny) CK(cudaMemsetAsync(e->sk_counters, 0, (size_t)(L + 1) * SK_BLOCK_INTS * 4, st));
@@ -1164,6 +1248,7 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
     a.u = a.l;
     memcpy(e->pinned, &a, sizeof a);
     CK(cudaMemcpyAsync(e->d_sargs, e->pinned, sizeof a, cudaMemcpyHostToDevice, st));
+    RC(prepare_step(e, st));  // the phase table is per row count
   }
   if (e->tp_fused_ready && e->R <= 8 && e->use_fused && max_new > 1) {
     // decode steps leave their (all-gathered) logits in the peer-visible buffer: re-point the sampler there
@@ -1193,6 +1278,7 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
     mix((uint64_t)(uintptr_t)e->sk_ws.p); mix((uint64_t)(uintptr_t)e->split_ws.p);
     // the meta carve-out places the sampler arguments, barriers and work table BEHIND the [B, max_new] sequence buffer, so
     // their addresses move with max_new even when every shape above is unchanged
+    mix((uint64_t)(e->step_ready ? 1 + e->step_launch.nw * 16 + e->step_launch.depth : 0)); mix((uint64_t)(uintptr_t)e->step_tab.p);
     mix((uint64_t)e->max_new); mix((uint64_t)(uintptr_t)e->d_sargs); mix((uint64_t)(uintptr_t)e->d_bar);
     mix((uint64_t)(uintptr_t)e->d_item_row); mix((uint64_t)(uintptr_t)e->d_seq_out);
     int per_step_launches = 0;

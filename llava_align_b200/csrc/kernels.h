@@ -67,6 +67,48 @@ struct GemvChain {
 };
 cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaStream_t stream);
 
+// ---------------------------------------------------------------- whole decode step in ONE persistent launch (R <= 4 rows)
+// decode_step.cu: a producer warp per CTA streams the weights of every projection with cp.async.bulk into shared-memory rings
+// while the consumer warps run  qkv_0 | per layer: attention | o | gate_up | down | next qkv (or lm_head)  behind grid barriers.
+enum StepPhaseKind { STEP_GEMV = 0, STEP_ATTN = 1 };
+struct StepPhase {
+  int kind;
+  GemvArgs g;            // STEP_GEMV
+  void* kcache;          // STEP_ATTN: this layer's K / V planes
+  void* vcache;
+};
+struct StepAttn {        // layer-independent part of the attention phases (see DecodeAttnArgs)
+  const float* qkv;
+  const int64_t* kv_off;
+  const int32_t* kv_cap;
+  const int32_t* pos;
+  const float* rope_cos;
+  const float* rope_sin;
+  void* out_bf16;
+  float* part_o;
+  float* part_ml;
+  int32_t* counters;
+  int heads, max_splits;
+  float scale;
+};
+struct StepArgs {
+  const StepPhase* phases;  // DEVICE array [nph]
+  int nph;
+  int skip_attn;            // bench: projections only (the barriers of the attention phases stay)
+  StepAttn attn;
+  unsigned* barrier;        // one monotonic grid-barrier counter, zero on entry
+  TpComm tpc;
+  unsigned long long* trace;  // debug: [grid][64 phases][8] globaltimer stamps of consumer thread 0, or null
+  int ring_depth, x_bytes;    // filled by launch_decode_step from the StepLaunch
+};
+struct StepLaunch {
+  int grid, nw, depth, x_bytes;
+  size_t smem;
+};
+bool step_kernel_supports(const StepPhase* host_phases, int nph, int R);
+cudaError_t plan_decode_step(const StepPhase* host_phases, int nph, int R, int num_sms, StepLaunch* out);
+cudaError_t launch_decode_step(const StepArgs& sa, const StepLaunch& L, int R, bool pdl, cudaStream_t stream);
+
 // ---------------------------------------------------------------- tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T
 enum GemmEpilogue {
   GEMM_OUT_F32 = 0,        // out_f32[row, col] = acc (+bias)

@@ -9,8 +9,9 @@ last-position logits at every step (teacher-forced on the oracle's tokens) and t
 
 A K-split, tile-width or KV-stride bug that only shows at H=4096 / ctx=607 fails here; the tiny-model tests cannot see it.
 Tolerance: bf16 activations and weights with fp32 accumulation against the fp32 oracle on the same bf16-representable
-weights; logits have std ~2.5.  Stated: max |dlogit| <= 0.10 on every stream at every step; greedy tokens exact unless the
-oracle's own top-2 margin of the combined scores is below 3x that."""
+weights; logits have std ~2.5.  Stated: max |dlogit| <= 0.10 on every stream at every step; greedy tokens exact, except that
+a row may leave the oracle's sequence at a step where the token it picked scores within 3x that tolerance of the oracle's
+best on the oracle's own combined scores (a near-tie: (1+a)l - a*cd amplifies a logit difference threefold at a = 1)."""
 import dataclasses
 
 import pytest
@@ -59,11 +60,9 @@ def _check(cfg, m, oracle, B, use_unk, use_none, n, T=32, seed=5):
     assert ref.stream_logits[0]["m"].std().item() > 1.0  # the comparison is not between two near-zero tensors
     out = m.generate(ids, images=img, use_dd=use_none, use_dd_unk=use_unk, cd_alpha=1.0, cd_beta=0.1, do_sample=True, top_k=1,
                      max_new_tokens=n, eos_token_id=None)
-    if not torch.equal(out, ref.sequences):
-        st = int((out != ref.sequences).nonzero()[:, 1].min()) - T
-        top2 = torch.topk(ref.scores[st], 2, dim=-1).values
-        margin = (top2[:, 0] - top2[:, 1]).min().item()
-        assert margin <= 3 * REAL_TOL, (st, margin, out[:, T:], ref.sequences[:, T:])
+    from helpers import greedy_divergence_is_near_tie
+    div = greedy_divergence_is_near_tie(out[:, T:].cpu(), ref.sequences[:, T:], ref.stream_logits, 1.0, 0.1, 3 * REAL_TOL)
+    assert len(div) <= max(1, (len(names) * B) // 8), div  # near-ties are the exception, not the rule
     print(f"real-width parity {cfg.name}: R={len(names) * B} rows, {n} steps, max |dlogit| = {worst:.4f}")
     return worst
 
