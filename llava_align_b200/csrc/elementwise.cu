@@ -51,12 +51,35 @@ cudaError_t launch_rmsnorm_bf16(const float* x, const void* w, float eps, void* 
 // 1024 threads per row: one float4 of the row per thread (H = 4096), so the residual and all split planes of a row are
 // requested at once -- the pass is a handful of dependent L2 round trips, not a bandwidth problem.
 constexpr int RR_THREADS = 1024;
+// bounded spin on a cross-GPU arrival counter (peer ranks bump it with red.sys after a system fence)
+__device__ __forceinline__ void tp_counter_wait(const unsigned* counter, unsigned per_epoch, const int32_t* epoch) {
+  const unsigned target = (unsigned)(*epoch + 1) * per_epoch;
+  unsigned spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= target) break;
+    if ((++spins & 0x3ffu) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (!t0) t0 = now;
+      else if (now - t0 > 30000000000ull) __trap();  // a peer never arrived: error return instead of a hung box
+    }
+  }
+  __threadfence_system();
+}
 __global__ void __launch_bounds__(RR_THREADS) reduce_rmsnorm_kernel(float* __restrict__ resid, const float* __restrict__ ws, int splits,
                                                                     int64_t plane_stride, const __nv_bfloat16* __restrict__ w, float eps,
-                                                                    __nv_bfloat16* __restrict__ out, int H) {
+                                                                    __nv_bfloat16* __restrict__ out, int H, const unsigned* wait,
+                                                                    unsigned wait_per_epoch, const int32_t* epoch) {
   __shared__ float red[33];
   pdl_wait();
   pdl_launch_dependents();
+  if (wait) {  // tensor parallel: the planes are the partial sums of all ranks, pushed into this rank's inbox by their GEMM epilogues
+    if (threadIdx.x == 0) tp_counter_wait(wait, wait_per_epoch, epoch);
+    __syncthreads();
+  }
   const int row = blockIdx.x;
   float* xr = resid + (size_t)row * H;
   const float* wr = ws + (size_t)row * H;
@@ -91,8 +114,17 @@ __global__ void __launch_bounds__(RR_THREADS) reduce_rmsnorm_kernel(float* __res
     *reinterpret_cast<uint2*>(out + (size_t)row * H + k) = o;
   }
 }
+__global__ void tp_wait_kernel(const unsigned* counter, unsigned per_epoch, const int32_t* epoch) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) tp_counter_wait(counter, per_epoch, epoch);
+}
+cudaError_t launch_tp_wait(const unsigned* counter, unsigned per_epoch, const int32_t* epoch, cudaStream_t stream) {
+  tp_wait_kernel<<<1, 32, 0, stream>>>(counter, per_epoch, epoch);
+  return cudaGetLastError();
+}
 cudaError_t launch_reduce_rmsnorm(float* resid, const float* ws, int splits, int rows, int H, const void* w, float eps, void* out,
-                                  cudaStream_t stream, bool pdl) {
+                                  cudaStream_t stream, bool pdl, const unsigned* wait, unsigned wait_per_epoch, const int32_t* epoch) {
   if (rows <= 0) return cudaSuccess;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(rows);
@@ -104,7 +136,7 @@ cudaError_t launch_reduce_rmsnorm(float* resid, const float* ws, int splits, int
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, reduce_rmsnorm_kernel, resid, ws, splits, (int64_t)rows * H, (const __nv_bfloat16*)w, eps,
-                            (__nv_bfloat16*)out, H);
+                            (__nv_bfloat16*)out, H, wait, wait_per_epoch, epoch);
 }
 
 // B operand of a row-scaled projection (decode_gemm.cu): out = bf16(x * g); the 1/rms factor is applied by the consumer.

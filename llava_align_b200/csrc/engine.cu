@@ -149,6 +149,7 @@ struct vdd_engine {
   size_t comm_bytes = 0;
   TpComm tpc;                      // filled by vdd_tp_comm_open
   bool tp_fused_ready = false;     // peers mapped: decode uses the in-kernel all-reduce instead of NCCL
+  int tp_max_rows = 0;             // rows the peer-visible inbox / logits areas were sized for (many-row decode path)
   int32_t* d_epoch = nullptr;      // decode steps since the last prefill (targets of the monotonic arrival counters)
   float* logits_cur = nullptr;     // where the last prefill / decode step left its logits
   // stats
@@ -220,7 +221,11 @@ extern "C" int vdd_create(const vdd_config* cfg, vdd_engine** out) {
   // the shared-tile fix-up cost ~14 us against a 15 us stream: profiles/r1_trace_skinny.json); opt-in until chained.
   e->use_skinny = getenv("VDD_SKINNY") != nullptr;
   e->use_fused = getenv("VDD_NO_FUSED") == nullptr;
-  e->use_step = getenv("VDD_NO_STEP") == nullptr;  // VDD_NO_STEP=1: one gemv_kernel chain + one attention launch per layer (round 1)
+  // Whole-step persistent kernel (decode_step.cu) vs one gemv_kernel chain + one attention launch per layer (decode_gemv.cu):
+  // measured on one GPU the per-layer launches stream faster (cp.async rings: 6.7 TB/s inside a projection against 5.7 TB/s
+  // for 4 KB TMA tiles at the same 128 KB in flight per SM), under tensor parallelism the single launch wins (the step is a
+  // chain of latencies there, not a stream).  VDD_STEP=1 / 0 overrides.
+  e->use_step = getenv("VDD_STEP") ? atoi(getenv("VDD_STEP")) != 0 : tp > 1;
   if (getenv("VDD_TRACE")) {
     cudaMalloc(&e->d_trace, (size_t)256 * 64 * 8 * 8);
     cudaMemset(e->d_trace, 0, (size_t)256 * 64 * 8 * 8);
@@ -459,6 +464,25 @@ static int do_gemm(vdd_engine* e, const void* a, const void* w, int M, int N, in
   e->launches++;
   if (ce != cudaSuccess)
     return fail(VDD_ERR_CUDA, "gemm M=%d N=%d K=%d: %s %s", M, N, K, cudaGetErrorString(ce), gemm_init_error() ? gemm_init_error() : "");
+  return VDD_OK;
+}
+// Row-parallel / vocab-parallel projection under tensor parallelism, many-row decode path: the tcgen05 GEMM's epilogue stores its
+// tiles into every rank's peer-visible buffer at byte offset `dst_off` (plus nothing else: the caller folds rank / slot / column
+// offsets into it) and every CTA bumps arrival counter `counter` on every rank.  *nctas = CTAs of the launch.
+static int gemm_tp_push(vdd_engine* e, const void* x, const void* w, int M, int N, int K, size_t dst_off, int64_t ldc, int counter,
+                        int* nctas, cudaStream_t st, bool pdl) {
+  GemmArgs g{x, w, M, N, K, GEMM_OUT_F32, nullptr, nullptr, nullptr, nullptr, ldc};
+  g.pdl = pdl;
+  g.tp_n = e->tpc.tp;
+  for (int k = 0; k < e->tpc.tp; ++k) {
+    g.tp_out[k] = (float*)(uintptr_t)(e->tpc.peers[k] + dst_off);
+    g.tp_cnt[k] = (unsigned*)(uintptr_t)e->tpc.peers[k] + counter;
+  }
+  g.tp_ctas = nctas;
+  cudaError_t ce = launch_gemm(g, st);
+  e->launches++;
+  if (ce != cudaSuccess)
+    return fail(VDD_ERR_CUDA, "tp gemm M=%d N=%d K=%d: %s %s", M, N, K, cudaGetErrorString(ce), gemm_init_error() ? gemm_init_error() : "");
   return VDD_OK;
 }
 // Zero-on-entry state of the skinny-GEMM chain launches of ONE decode step (cleared by a single memset per step):
@@ -712,7 +736,9 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
     const size_t o_res = carve((size_t)R * H * 4), o_qkv = carve((size_t)R * 3 * Hl * 4),
-                 o_po = carve((size_t)R * e->heads_l * e->max_splits * 128 * 4), o_pm = carve((size_t)R * e->heads_l * e->max_splits * 8);
+                 // split partials: 64-token splits for decode_attn_kernel, 32-token splits for the whole-step kernel (twice as many)
+                 o_po = carve((size_t)R * e->heads_l * (2 * e->max_splits + 1) * 128 * 4),
+                 o_pm = carve((size_t)R * e->heads_l * (2 * e->max_splits + 1) * 8);
     RC(ensure(e, e->dec_f32, o));
     char* b = (char*)e->dec_f32.p;
     e->resid_d = (float*)(b + o_res); e->qkv_d = (float*)(b + o_qkv); e->part_o = (float*)(b + o_po); e->part_ml = (float*)(b + o_pm);
@@ -905,6 +931,7 @@ static int prepare_step(vdd_engine* e, cudaStream_t st) {
   }
   if (!step_kernel_supports(ph.data(), (int)ph.size(), R)) return VDD_OK;  // odd shapes keep the per-layer launches
   if (plan_decode_step(ph.data(), (int)ph.size(), R, e->num_sms, &e->step_launch) != cudaSuccess) return VDD_OK;
+  if (step_build_tmaps(ph.data(), (int)ph.size()) != cudaSuccess) return VDD_OK;
   RC(ensure(e, e->step_tab, ph.size() * sizeof(StepPhase)));
   CK(cudaMemcpyAsync(e->step_tab.p, ph.data(), ph.size() * sizeof(StepPhase), cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));  // the host vector goes out of scope
@@ -940,7 +967,8 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     sa.skip_attn = projections_only ? 1 : 0;
     sa.attn.qkv = e->qkv_d; sa.attn.kv_off = e->d_kv_off; sa.attn.kv_cap = e->d_kv_cap; sa.attn.pos = e->d_pos;
     sa.attn.rope_cos = e->rope_cos; sa.attn.rope_sin = e->rope_sin; sa.attn.out_bf16 = e->attn_d; sa.attn.part_o = e->part_o;
-    sa.attn.part_ml = e->part_ml; sa.attn.counters = e->d_counters; sa.attn.heads = e->heads_l; sa.attn.max_splits = e->max_splits;
+    sa.attn.part_ml = e->part_ml; sa.attn.counters = e->d_counters; sa.attn.heads = e->heads_l;
+    sa.attn.max_splits = (e->max_len + e->max_new + 31) / 32;  // 32-token splits (<= 2 * max_splits: the partial buffers are sized for it)
     sa.attn.scale = 0.08838834764831845f;
     sa.barrier = e->d_bar;
     if (tpf) sa.tpc = e->tpc;
@@ -971,7 +999,14 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
   }
   // 8 < R on one GPU, square-tile GEMMs: every launch of the layer is programmatically serialised (set-up overlaps the
   // predecessor's tail), and the split-K reduction of o_proj / down_proj is folded into the RMSNorm pass that follows it
-  const bool wide = R > 8 && !tp && !skinny;
+  // ... and under tensor parallelism with mapped peers: same launches, the all-reduce rides in the o_proj / down_proj epilogues
+  // (peer stores + arrival counters) and in the reduce + RMSNorm pass that follows them; the logits are gathered the same way
+  const bool tpm = tp && tpf && R > 8 && R <= e->tp_max_rows && getenv("VDD_TP_MANY_NCCL") == nullptr;
+  const bool wide = R > 8 && !skinny && (!tp || tpm);
+  const size_t slot_bytes = (size_t)c.tp_size * e->tp_max_rows * H * 4;   // one inbox slot on every rank
+  const size_t plane_off = (size_t)c.tp_rank * R * H * 4;                 // this rank's plane inside a slot
+  const float* inbox_local = tpm ? (const float*)((const char*)e->comm_buf + e->tpc.off_inbox) : nullptr;
+  const unsigned* cnt_local = tpm ? (const unsigned*)e->comm_buf : nullptr;
   if (wide) LK(e, launch_rmsnorm_bf16(e->resid_d, e->lw[0].ln1, c.rms_eps, e->xn_d, R, H, nullptr, st, pdl));
   for (int l = 0; l < L; ++l) {
     const LayerW& w = e->lw[l];
@@ -1026,6 +1061,18 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
       RC(do_skinny_chain(e, ch, 1 + l, st));
       continue;
     }
+    if (wide && tpm) {
+      int nct = 0;
+      RC(gemm_tp_push(e, e->attn_d, w.wo, R, H, Hl, (size_t)e->tpc.off_inbox + plane_off, H, 2 * l, &nct, st, pdl));
+      LK(e, launch_reduce_rmsnorm(e->resid_d, inbox_local, c.tp_size, R, H, w.ln2, c.rms_eps, e->xn_d, st, pdl, cnt_local + 2 * l,
+                                  (unsigned)(c.tp_size * nct), e->d_epoch));
+      RC(do_gemm(e, e->xn_d, w.wgu, R, 2 * Il, H, GEMM_OUT_SWIGLU, nullptr, nullptr, nullptr, e->h_d, Il, st, pdl));
+      RC(gemm_tp_push(e, e->h_d, w.wdown, R, H, Il, (size_t)e->tpc.off_inbox + slot_bytes + plane_off, H, 2 * l + 1, &nct, st, pdl));
+      LK(e, launch_reduce_rmsnorm(e->resid_d, (const float*)((const char*)inbox_local + slot_bytes), c.tp_size, R, H,
+                                  l + 1 < L ? e->lw[l + 1].ln1 : e->final_norm, c.rms_eps, e->xn_d, st, pdl, cnt_local + 2 * l + 1,
+                                  (unsigned)(c.tp_size * nct), e->d_epoch));
+      continue;
+    }
     if (wide) {
       int sp = 0;
       RC(do_gemm(e, e->attn_d, w.wo, R, H, Hl, GEMM_OUT_ADD_F32, nullptr, nullptr, e->resid_d, nullptr, H, st, pdl, &sp));
@@ -1059,6 +1106,13 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
   if (!fused && !skinny) {
     if (R <= 8) {
       LK(e, launch_gemv(head_args(), e->num_sms, pdl, st));
+    } else if (wide && tpm) {
+      // vocab-parallel lm_head: this rank's column block lands in every rank's gathered logits; one waiting thread holds the
+      // stream until all blocks are there
+      int nct = 0;
+      RC(gemm_tp_push(e, e->xn_d, e->lm_head, R, e->Vl, H, (size_t)e->tpc.off_logits + (size_t)c.tp_rank * e->Vl * 4, c.vocab_size, 2 * L,
+                      &nct, st, pdl));
+      LK(e, launch_tp_wait(cnt_local + 2 * L, (unsigned)(c.tp_size * nct), e->d_epoch, st));
     } else if (wide) {
       RC(do_gemm(e, e->xn_d, e->lm_head, R, e->Vl, H, GEMM_OUT_F32, nullptr, nullptr, lg, nullptr, e->Vl, st, pdl));
     } else {
@@ -1066,8 +1120,8 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
       RC(gemm(e->xn_d, e->lm_head, e->Vl, H, GEMM_OUT_F32, lg, nullptr, e->Vl));
     }
   }
-  if (tp && !(tpf && fused)) RC(tp_gather_logits(e, st));
-  if (!projections_only) e->logits_cur = (tpf && fused) ? (float*)((char*)e->comm_buf + e->tpc.off_logits) : (float*)e->logits.p;
+  if (tp && !(tpf && fused) && !tpm) RC(tp_gather_logits(e, st));
+  if (!projections_only) e->logits_cur = ((tpf && fused) || tpm) ? (float*)((char*)e->comm_buf + e->tpc.off_logits) : (float*)e->logits.p;
   return VDD_OK;
 }
 
@@ -1250,7 +1304,9 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
     CK(cudaMemcpyAsync(e->d_sargs, e->pinned, sizeof a, cudaMemcpyHostToDevice, st));
     RC(prepare_step(e, st));  // the phase table is per row count
   }
-  if (e->tp_fused_ready && e->R <= 8 && e->use_fused && max_new > 1) {
+  const bool tp_many = e->tp_fused_ready && e->R > 8 && e->R <= e->tp_max_rows && !(e->use_skinny && e->sk_counters) &&
+                       getenv("VDD_TP_MANY_NCCL") == nullptr;
+  if (e->tp_fused_ready && ((e->R <= 8 && e->use_fused) || tp_many) && max_new > 1) {
     // decode steps leave their (all-gathered) logits in the peer-visible buffer: re-point the sampler there
     CK(cudaStreamSynchronize(st));
     float* cl = (float*)((char*)e->comm_buf + e->tpc.off_logits);
@@ -1399,8 +1455,13 @@ extern "C" int vdd_tp_comm_handle(vdd_engine* e, void* handle64) {
   if (!e || !handle64) return fail(VDD_ERR_ARG, "null argument");
   if (e->c.tp_size <= 1 || e->c.tp_size > 8) return fail(VDD_ERR_UNSUPPORTED, "peer communication supports 2..8 ranks");
   if (!e->comm_buf) {
-    const size_t inbox = (size_t)2 * e->c.tp_size * 8 * e->c.hidden_size * 4;
-    const size_t logits = (size_t)8 * e->c.vocab_size * 4;
+    // [2 slots][tp source planes][rows][H] fp32 partial sums + [rows][V] fp32 gathered logits; rows = 8 for the GEMV / whole-step
+    // kernels, up to VDD_TP_MAX_ROWS (default 256) for the tensor-core decode path of BASELINE configs[3..4]
+    int mr = getenv("VDD_TP_MAX_ROWS") ? atoi(getenv("VDD_TP_MAX_ROWS")) : 256;
+    if (mr < 8) mr = 8;
+    e->tp_max_rows = mr;
+    const size_t inbox = (size_t)2 * e->c.tp_size * mr * e->c.hidden_size * 4;
+    const size_t logits = (size_t)mr * e->c.vocab_size * 4;
     e->tpc.off_inbox = 4096;
     e->tpc.off_logits = 4096 + (long long)align_up(inbox, 256);
     e->comm_bytes = (size_t)e->tpc.off_logits + logits;

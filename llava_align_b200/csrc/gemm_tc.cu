@@ -41,7 +41,17 @@ struct GemmEpi {
   float* out_f32;
   __nv_bfloat16* out_bf16;
   int64_t ldc;
+  int tp;               // > 1: GEMM_OUT_F32 tiles go to every rank (peer memory over NVLink) and every CTA signals every rank
+  float* tp_out[8];
+  unsigned* tp_cnt[8];
 };
+// end of a CTA's work under tensor parallelism: publish its peer stores, then bump the arrival counter on every rank
+__device__ __forceinline__ void gm_tp_arrive(const GemmEpi& ep) {
+  if (ep.tp > 1 && threadIdx.x == 0) {
+    __threadfence_system();
+    for (int k = 0; k < ep.tp; ++k) asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(ep.tp_cnt[k]) : "memory");
+  }
+}
 
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + expf(-1.702f * x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -55,7 +65,15 @@ __device__ __forceinline__ void gm_store16(const GemmEpi& ep, int64_t orow, int 
 #pragma unroll
     for (int i = 0; i < 8; ++i) { v[2 * i] += bf16lo(bw[i]); v[2 * i + 1] += bf16hi(bw[i]); }
   }
-  if (ep.mode == GEMM_OUT_F32 || ep.mode == GEMM_OUT_ADD_F32) {
+  if (ep.tp > 1) {
+    // tensor parallel (GEMM_OUT_F32): the tile goes straight into every rank's buffer -- this rank's plane of the all-reduce
+    // inbox, or its column block of the gathered logits; the bases are pre-offset by the host
+    for (int k = 0; k < ep.tp; ++k) {
+      float4* o = reinterpret_cast<float4*>(ep.tp_out[k] + orow * ep.ldc + col);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+  } else if (ep.mode == GEMM_OUT_F32 || ep.mode == GEMM_OUT_ADD_F32) {
     // split-K: slice z writes its partial to scratch plane z; the planes are added in order by a later pass
     float4* o = reinterpret_cast<float4*>(ep.out_f32 + (ep.splits > 1 ? (int64_t)zplane * ep.M * ep.ldc : 0) + orow * ep.ldc + col);
 #pragma unroll
@@ -201,6 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tcgen05_fence_before();
   __syncthreads();
+  gm_tp_arrive(ep);
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
@@ -329,6 +348,7 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   tcgen05_fence_before();
   __syncthreads();
+  gm_tp_arrive(ep);
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
@@ -387,6 +407,9 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   ep.out_f32 = a.out_f32;
   ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
   ep.ldc = a.ldc;
+  ep.tp = a.tp_n > 1 ? a.tp_n : 0;
+  for (int k = 0; k < 8; ++k) { ep.tp_out[k] = a.tp_out[k]; ep.tp_cnt[k] = a.tp_cnt[k]; }
+  if (ep.tp && (a.epilogue != GEMM_OUT_F32 || a.row_map || a.bias || a.tp_n > 8)) return cudaErrorInvalidValue;
   dim3 grid((a.N + GM_BN - 1) / GM_BN, (a.M + GM_BM - 1) / GM_BM);
   ep.splits = 1;
   if (a.epilogue == GEMM_OUT_ADD_F32 && a.M <= GM_BM && a.split_ws && !a.row_map && !a.bias) {
@@ -430,6 +453,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     cfg.attrs = atw;
     cfg.numAttrs = a.pdl ? 1 : 0;
     if (a.defer_reduce) *a.defer_reduce = 0;
+    if (a.tp_ctas) *a.tp_ctas = (int)cfg.gridDim.x;
     return cudaLaunchKernelEx(&cfg, gemm_tc_wide_kernel, ta, tb, ep, m_tiles, n_tiles);
   }
   ep.bn = GM_BN;
@@ -458,6 +482,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     cfg.dynamicSmemBytes = gm_smem(3);
   }
   cfg.gridDim = grid;
+  if (a.tp_ctas) *a.tp_ctas = (int)(grid.x * grid.y * grid.z);
   if (!make_tmap(&ta, a.a, a.M, a.K) || !make_tmap(&tb, a.w, a.N, a.K, ep.bn)) return cudaErrorInvalidValue;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];

@@ -76,6 +76,11 @@ struct StepPhase {
   GemvArgs g;            // STEP_GEMV
   void* kcache;          // STEP_ATTN: this layer's K / V planes
   void* vcache;
+  // STEP_GEMV: TMA descriptors (CUtensorMap, 128 B each) of the weight matrix seen as [N][K/64][64] bf16 with 128-byte swizzle and
+  // a box of 64 x 4 x {2,4,6,8} rows: ONE cp.async.bulk.tensor per 4 KB step (8 rows x 256 k), the last group of a CTA's band
+  // (bands are pairs of rows) fetched with the narrower box instead of over-fetching the neighbour's rows
+  alignas(64) unsigned char tmap[4][128];
+  int tmap_plain;        // 1: K is not a multiple of 64 (7B at TP=8): plain 2-D box of 256 k x rows, no swizzle (2-way bank conflicts)
 };
 struct StepAttn {        // layer-independent part of the attention phases (see DecodeAttnArgs)
   const float* qkv;
@@ -100,12 +105,15 @@ struct StepArgs {
   TpComm tpc;
   unsigned long long* trace;  // debug: [grid][64 phases][8] globaltimer stamps of consumer thread 0, or null
   int ring_depth, x_bytes;    // filled by launch_decode_step from the StepLaunch
+  int l2_ahead;               // steps per warp kept in flight towards L2 beyond the shared-memory ring
+  int l2_hint;                // 1: weights are loaded with the L2 evict-first policy
 };
 struct StepLaunch {
   int grid, nw, depth, x_bytes;
   size_t smem;
 };
 bool step_kernel_supports(const StepPhase* host_phases, int nph, int R);
+cudaError_t step_build_tmaps(StepPhase* host_phases, int nph);  // fills tmap[] of every STEP_GEMV phase (host side, before upload)
 cudaError_t plan_decode_step(const StepPhase* host_phases, int nph, int R, int num_sms, StepLaunch* out);
 cudaError_t launch_decode_step(const StepArgs& sa, const StepLaunch& L, int R, bool pdl, cudaStream_t stream);
 
@@ -134,6 +142,14 @@ struct GemmArgs {
   bool pdl = false;           // launch with programmatic stream serialization (the kernel waits before touching dependent data)
   int* defer_reduce = nullptr;  // non-null: leave the split-K planes in split_ws and report their number here (0 = accumulated
                                 // directly); the caller folds the reduction into its next pass (launch_reduce_rmsnorm)
+  // Tensor parallel, GEMM_OUT_F32 only: the epilogue stores every output tile into ALL ranks' buffers over NVLink peer memory
+  // (tp_out[k] = where this rank's tile lands on rank k: its partial plane of the all-reduce inbox, or its column block of the
+  // gathered logits), then every CTA bumps the arrival counter tp_cnt[k] on every rank (system fence + red.sys).  The consumer
+  // kernel on each rank waits for tp_n * (*tp_ctas) arrivals per decode step.  No NCCL call, no extra launch.
+  int tp_n = 0;
+  float* tp_out[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned* tp_cnt[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int* tp_ctas = nullptr;       // out: CTAs of the launch (arrivals this rank contributes per peer)
 };
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
 const char* gemm_init_error();
@@ -226,8 +242,12 @@ cudaError_t launch_attn_probs(const AttnProbsArgs& a, cudaStream_t stream);
 cudaError_t launch_rmsnorm_bf16(const float* x, const void* w_bf16, float eps, void* out_bf16, int rows, int H,
                                 const int32_t* row_idx, cudaStream_t stream, bool pdl = false);
 // resid[r] += sum_z ws[z][r] (split-K planes of a residual GEMM, plane pitch rows*H), then out[r] = bf16(rmsnorm(resid[r]) * w)
+// wait != null: the planes are the tensor-parallel inbox; the kernel first waits until *wait >= (*epoch + 1) * wait_per_epoch
 cudaError_t launch_reduce_rmsnorm(float* resid, const float* ws, int splits, int rows, int H, const void* w_bf16, float eps,
-                                  void* out_bf16, cudaStream_t stream, bool pdl);
+                                  void* out_bf16, cudaStream_t stream, bool pdl, const unsigned* wait = nullptr,
+                                  unsigned wait_per_epoch = 0, const int32_t* epoch = nullptr);
+// one thread spins until *counter >= (*epoch + 1) * per_epoch (all ranks' logit blocks have landed), then the stream goes on
+cudaError_t launch_tp_wait(const unsigned* counter, unsigned per_epoch, const int32_t* epoch, cudaStream_t stream);
 cudaError_t launch_layernorm(const float* x, const void* w_bf16, const void* b_bf16, float eps, void* out_bf16,
                              float* out_f32, int rows, int H, const int32_t* row_idx, cudaStream_t stream);
 cudaError_t launch_embed_rows(const void* table_bf16, const int32_t* tok, const int32_t* img_row,
