@@ -41,6 +41,9 @@ def parse():
                          "all-reduce inside the decode kernels over NVLink peer memory), strong scaling; dp = one independent request "
                          "stream per GPU (how the reference itself uses several GPUs, scripts/pope/run_dataset.sh:14-32), no collective")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[2] (batch 32) block of the JSON line")
+    ap.add_argument("--flags", default="both", choices=["both", "unk", "dd"],
+                    help="debias streams: both = use_dd + use_dd_unk (3 fused streams, BASELINE configs[1,2,4]); unk = use_dd_unk only "
+                         "(2 streams, configs[3]); dd = use_dd only")
     ap.add_argument("--profile", action="store_true", help="under ncu: the device-resident leg only, no extra launches")
     return ap.parse_args()
 
@@ -150,19 +153,31 @@ def run_reference(a):
     _emit(line)
 
 
+def stream_flags(a):
+    """(use_dd_unk, use_dd, number of fused streams, text)"""
+    return {"both": (True, True, 3, "use_dd+use_dd_unk (3 fused streams)"), "unk": (True, False, 2, "use_dd_unk (2 fused streams)"),
+            "dd": (False, True, 2, "use_dd (2 fused streams)")}[a.flags]
+
+
 def workload_config(a, cfg, n, mode="dp"):
-    if a.batch == 1 and a.prompt_len == 32 and a.new_tokens == 256:
+    is13 = "13b" in cfg.name
+    if not is13 and a.batch == 1 and a.prompt_len == 32 and a.new_tokens == 256 and a.flags == "both":
         which = "BASELINE.json configs[1]"
-    elif a.batch == 32:
+    elif not is13 and a.batch == 32 and a.flags == "both":
         which = "BASELINE.json configs[2] shape (POPE-like batch of 32)"
+    elif is13 and a.batch == 8 and a.flags == "unk":
+        which = "BASELINE.json configs[3] shape (13B, batch 8, use_dd_unk)"
+    elif is13 and a.batch == 64 and a.flags == "both":
+        which = "BASELINE.json configs[4] shape (13B, batch 64, both dd streams)"
     else:
         which = "custom shape (not a BASELINE.json config)"
     return {"workload": f"{which}: {cfg.name} bf16 random-init, batch {a.batch}, 1 synthetic "
-                        f"{cfg.image_size}px image, {a.prompt_len}-token prompt, {a.new_tokens} new tokens, use_dd+use_dd_unk "
-                        f"(3 fused streams), cd_alpha=1 cd_beta=0.1, temperature-1 sampling, EOS disabled",
-            "global_batch": a.batch, "new_tokens": a.new_tokens, "prompt_len": a.prompt_len, "streams": 3,
+                        f"{cfg.image_size}px image, {a.prompt_len}-token prompt, {a.new_tokens} new tokens, {stream_flags(a)[3]}, "
+                        f"cd_alpha=1 cd_beta=0.1, temperature-1 sampling, EOS disabled",
+            "global_batch": a.batch, "new_tokens": a.new_tokens, "prompt_len": a.prompt_len, "streams": stream_flags(a)[2],
             "parallelism": "single GPU" if n == 1 else (
-                f"tp{n} (heads/FFN/vocab split; decode: all-reduce and logit all-gather inside the projection kernel over NVLink peer memory; prefill: NCCL)" if mode == "tp"
+                f"tp{n}: ONE request stream sharded over {n} GPUs (heads / FFN columns / vocab split; decode: all-reduce and logit "
+                f"all-gather inside the projection kernels over NVLink peer memory, no NCCL call; prefill: NCCL all-reduce)" if mode == "tp"
                 else f"dp{n}: {n} independent replicas, one request stream per GPU, no data-path collective"),
             "l2_policy": "inputs larger than L2: every step streams the 13.2 GB of weights (L2 = 126 MB); no flush needed"}
 
@@ -261,13 +276,14 @@ def main():
         params = E.make_sample_params(cd_alpha=1.0, cd_beta=0.1, use_contrast=True, eos_token_id=None)
         g = torch.Generator(device=dev).manual_seed(1234)
         q = torch.empty(n_new, B, V, device=dev).exponential_(1, generator=g)  # identical on every TP rank
-        dev_fn = lambda: eng.generate(ids, img_dev, True, True, params, n_new, q, None)
+        use_unk, use_none, S, _ = stream_flags(a)
+        dev_fn = lambda: eng.generate(ids, img_dev, use_unk, use_none, params, n_new, q, None)
         ms, launches = timed(dev_fn, warm, steps)
         tm = eng.last_timings()
         out = {"value": replicas * B * n_new * steps / (ms / 1e3), "ms_per_step": ms / steps, "launches": int(launches) * replicas,
                "e2e": None}
         if with_e2e:
-            gen_kw = dict(images=img_pinned, images_cd=None, cd_alpha=1.0, cd_beta=0.1, use_dd=True, use_dd_unk=True, do_sample=True,
+            gen_kw = dict(images=img_pinned, images_cd=None, cd_alpha=1.0, cd_beta=0.1, use_dd=use_none, use_dd_unk=use_unk, do_sample=True,
                           temperature=1.0, top_p=None, top_k=None, max_new_tokens=n_new, use_cache=True, eos_token_id=None)
             e2e_fn = lambda: model.generate(ids_pinned, **gen_kw)  # TP: generate() broadcasts rank 0's variates itself
             ms2, _ = timed(e2e_fn, 1, steps)
@@ -290,8 +306,8 @@ def main():
         out["chain_ms"] = max(e0.elapsed_time(e1) / reps, 1e-6)
         out["chain_reps"] = reps
         # whole decode step against its own algorithmic bytes (weights once + KV of all rows at mid-run + logits)
-        ctx_mid = (T + cfg.num_patches - 1) + T + (T - 1) + 3 * (n_new // 2)
-        step_bytes = proj_bytes + B * ctx_mid * kv_tok + 3 * B * V * 4
+        ctx_mid = (T + cfg.num_patches - 1) + (T if use_unk else 0) + ((T - 1) if use_none else 0) + S * (n_new // 2)
+        step_bytes = proj_bytes + B * ctx_mid * kv_tok + S * B * V * 4 // tp
         step_ms = tm["decode_ms"] / max(1, n_new - 1)
         out["decode_step"] = {"ms_per_token_step": step_ms, "tokens_per_s_decode_only": B * 1e3 / step_ms if step_ms > 0 else None,
                               "algorithmic_GB_per_step": step_bytes / 1e9,
@@ -311,7 +327,8 @@ def main():
 
     # ---- roofline of the dominant kernel (the decode projections), timed live with CUDA events
     n_proj = 4 * L + 1
-    fused_rows = 3 * B <= 8  # the GEMV chain is the R <= 8 path; larger batches decode through gemm_tc_kernel
+    S_streams = stream_flags(a)[2]
+    fused_rows = S_streams * B <= 8  # the GEMV chain is the R <= 8 path; larger batches decode through gemm_tc_kernel
     n_gemv, chain_ms, reps = m["chain_launches"], m["chain_ms"], m["chain_reps"]
     achieved = proj_bytes / (chain_ms / 1e3) / 1e9
     traffic = None
@@ -325,7 +342,7 @@ def main():
                 "how": f"CUDA events around {reps} back-to-back replays of one decode step's {n_gemv} projection launches "
                        f"({n_proj} projections, {proj_bytes / 1e9:.2f} GB of weights per GPU)"}
     if not fused_rows:
-        roofline.update({"kernel": f"vdd::gemm_tc_kernel (tcgen05; decode projections of {3 * B} fused rows: qkv, o, gate_up, down per layer + "
+        roofline.update({"kernel": f"vdd::gemm_tc_kernel (tcgen05; decode projections of {S_streams * B} fused rows: qkv, o, gate_up, down per layer + "
                                    f"lm_head, with the split-K reduce + RMSNorm passes between them)", "traffic": None,
                          "how": f"CUDA events around {reps} back-to-back replays of one decode step's projection launches "
                                 f"({n_gemv} launches incl. {2 * L + 1} norm passes, {proj_bytes / 1e9:.2f} GB of weights per GPU)"})

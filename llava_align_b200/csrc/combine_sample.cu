@@ -434,9 +434,180 @@ combine_sample_cluster_kernel(const SampleArgs byval, const SampleArgs* dptr) {
   cl.sync();  // nobody leaves while a peer may still read its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------ row-streaming fast path
+// Many rows (B >= 8) and no ordering needed: one PERSISTENT CTA per SM walks the rows.  A row's main-stream logits are bulk-copied
+// (cp.async.bulk, one 128 KB request) into shared memory, where they stay for the row maximum, are overwritten in place by the
+// combined scores and serve the scores_out write; the debias streams and the race variates are streamed ONCE with 16-byte loads,
+// eighteen per thread in flight (~150 KB per SM), and consumed on the fly.  Two block reductions per row (three with top_k = 1)
+// instead of four cluster-wide ones, no DSMEM, no 14 waves of 8-CTA clusters.  Per-element arithmetic and its order are those of
+// the kernels above => bit-identical scores and tokens.
+constexpr int CR_THREADS = 512, CR_UNROLL = 6;
+
+__device__ __forceinline__ unsigned long long race_key(float v, int e) {
+  unsigned kb = __float_as_uint(v);
+  kb = (kb & 0x80000000u) ? ~kb : (kb | 0x80000000u);
+  return ((unsigned long long)kb << 32) | (unsigned)(0x7fffffff - e);
+}
+
+__global__ void __launch_bounds__(CR_THREADS, 1) combine_sample_rows_kernel(const SampleArgs byval, const SampleArgs* dptr) {
+  extern __shared__ __align__(16) float srow[];  // V floats
+  __shared__ float redf[33];
+  __shared__ unsigned long long best_s;
+  __shared__ __align__(8) uint64_t bar;
+  const SampleArgs& a = dptr ? *dptr : byval;
+  const int tid = threadIdx.x;
+  const int V = a.V, nv4 = V >> 2;
+  const int step = a.step_ptr ? *a.step_ptr : 0;
+  const bool topk1 = a.top_k == 1;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    const float* l = a.l + (int64_t)b * a.ld;
+    const float* u = a.u ? a.u + (int64_t)b * a.ld : nullptr;
+    const float* d = a.d ? a.d + (int64_t)b * a.ld : nullptr;
+    const int64_t so = ((int64_t)step * a.B + b) * V;
+    const float* q = a.q ? a.q + so : nullptr;
+    float* scores_out = a.scores_out ? a.scores_out + so : nullptr;
+    const bool contrast = a.use_contrast && (u || d);
+    if (tid == 0) {
+      fence_proxy_async();  // the previous row's generic accesses to srow are ordered before this async write
+      mbar_arrive_expect_tx(&bar, (uint32_t)V * 4u);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(srow)), "l"(reinterpret_cast<uint64_t>(l)), "r"((uint32_t)V * 4u), "r"(smem_u32(&bar)) : "memory");
+    }
+    // the debias streams and the variates do not depend on the row in shared memory: their first chunk is requested before the wait
+    const float4* u4 = reinterpret_cast<const float4*>(u);
+    const float4* d4 = reinterpret_cast<const float4*>(d);
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+    float4 uu[CR_UNROLL], dd[CR_UNROLL], qq[CR_UNROLL];
+    auto load_chunk = [&](int i0) {
+#pragma unroll
+      for (int j = 0; j < CR_UNROLL; ++j) {  // every load of the chunk is issued before anything is consumed
+        const int i = i0 + j * CR_THREADS;
+        const bool ok = i < nv4;
+        uu[j] = (contrast && u && ok) ? __ldg(u4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dd[j] = (contrast && d && ok) ? __ldg(d4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        qq[j] = (q && !topk1 && ok) ? __ldg(q4 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+    };
+    load_chunk(tid);
+    mbar_wait(&bar, parity);
+    parity ^= 1u;
+    float4* s4 = reinterpret_cast<float4*>(srow);
+    // ---- row maximum of the raw main-stream logits (vcd_sample.py:191)
+    float mx = -INFINITY;
+    for (int i = tid; i < nv4; i += CR_THREADS) {
+      const float4 x = s4[i];
+      mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+    }
+    mx = block_reduce<true>(mx, redf);
+    const float cutoff = __fadd_rn(a.log_beta, mx);
+    const float a1 = a.one_plus_alpha, al = a.alpha, temp = a.temperature;
+    // ---- combine + mask (+ temperature) in place; the race rides along unless top_k = 1 has to mask first
+    unsigned long long best = 0ull;
+    float m2 = -INFINITY;
+    for (int i0 = tid; i0 < nv4; i0 += CR_THREADS * CR_UNROLL) {
+      if (i0 != tid) load_chunk(i0);
+#pragma unroll
+      for (int j = 0; j < CR_UNROLL; ++j) {
+        const int i = i0 + j * CR_THREADS;
+        if (i < nv4) {
+          const float4 lv = s4[i];
+          float v[4] = {lv.x, lv.y, lv.z, lv.w};
+          const float cu[4] = {uu[j].x, uu[j].y, uu[j].z, uu[j].w}, cdv[4] = {dd[j].x, dd[j].y, dd[j].z, dd[j].w};
+          const float qv[4] = {qq[j].x, qq[j].y, qq[j].z, qq[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (contrast) {
+              const float c = (u && d) ? __fmul_rn(__fadd_rn(cu[e], cdv[e]), 0.5f) : (u ? cu[e] : cdv[e]);
+              const float sc = __fsub_rn(__fmul_rn(a1, v[e]), __fmul_rn(al, c));
+              v[e] = v[e] < cutoff ? -INFINITY : sc;
+            }
+            if (temp != 1.0f) v[e] = __fdiv_rn(v[e], temp);
+            if (topk1) m2 = fmaxf(m2, v[e]);
+            else best = max(best, race_key(q ? v[e] - logf(qv[e]) : v[e], i * 4 + e));
+          }
+          s4[i] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+    if (topk1) {  // TopK(1): everything below the row maximum goes (ties stay), then the race among the survivors
+      m2 = block_reduce<true>(m2, redf);
+      for (int i = tid; i < nv4; i += CR_THREADS) {
+        const float4 sv = s4[i];
+        float v[4] = {sv.x, sv.y, sv.z, sv.w};
+        bool any = false;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (v[e] < m2) v[e] = -INFINITY;
+          else any = true;
+        }
+        s4[i] = make_float4(v[0], v[1], v[2], v[3]);
+        if (any) {
+          float4 qv4 = q ? __ldg(q4 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float qv[4] = {qv4.x, qv4.y, qv4.z, qv4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) best = max(best, race_key(q ? v[e] - logf(qv[e]) : v[e], i * 4 + e));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) best = max(best, race_key(-INFINITY, i * 4 + e));
+        }
+      }
+    }
+    // ---- scores (vcd_sample.py:200): every thread re-reads what it wrote itself
+    if (scores_out) {
+      float4* o4 = reinterpret_cast<float4*>(scores_out);
+      for (int i = tid; i < nv4; i += CR_THREADS) o4[i] = s4[i];
+    }
+    // ---- arg-max of the race, lowest index on ties
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+      best = t > best ? t : best;
+    }
+    if (tid == 0) best_s = 0ull;
+    __syncthreads();
+    if ((tid & 31) == 0) atomicMax(&best_s, best);
+    __syncthreads();
+    if (tid == 0) {
+      long long tok = 0x7fffffff - (int)(best_s & 0xffffffffull);
+      if (a.eos >= 0 && a.unfinished) {
+        const int unf = a.unfinished[b];
+        tok = tok * unf + a.pad * (1 - unf);
+        a.unfinished[b] = (unf != 0 && tok != a.eos) ? 1 : 0;
+      }
+      if (a.tokens_out) a.tokens_out[b] = tok;
+      if (a.seq_out) a.seq_out[(int64_t)b * a.seq_ld + step] = tok;
+    }
+    __syncthreads();  // srow and best_s are reused by the next row
+  }
+}
+
 cudaError_t launch_combine_sample(const SampleArgs& args, const SampleArgs* dptr, int B, int V, cudaStream_t stream) {
   // host copy of the warper settings decides the kernel (the device struct, when used, holds the same values)
   const bool needs_order = args.top_p < 1.0f || (args.top_k > 1 && args.top_k < V);
+  // measured (us per launch, 3 streams + q): B = 32: cluster 10.9 / rows 15.3;  B = 64: 13.6 / 15.5;  B = 1024: 268 / 123
+  static const int rows_min = getenv("VDD_K8_ROWS_MIN") ? atoi(getenv("VDD_K8_ROWS_MIN")) : 96;
+  const bool aligned = (V % 4) == 0 && (args.ld % 4) == 0 && !((uintptr_t)args.l & 15) && !((uintptr_t)args.u & 15) &&
+                       !((uintptr_t)args.d & 15) && !((uintptr_t)args.q & 15) && !((uintptr_t)args.scores_out & 15);
+  if (!needs_order && aligned && B >= rows_min && V <= 32768) {
+    static int num_sms = 0;
+    static bool attr = false;
+    if (!attr) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaError_t e = cudaFuncSetAttribute(combine_sample_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4);
+      if (e != cudaSuccess) return e;
+      attr = true;
+    }
+    combine_sample_rows_kernel<<<B < num_sms ? B : num_sms, CR_THREADS, (size_t)V * 4, stream>>>(args, dptr);
+    return cudaGetLastError();
+  }
   if (!needs_order && V <= CC_CL * CC_THREADS * CC_ITEMS && getenv("VDD_K8_SINGLE_CTA") == nullptr) {
     combine_sample_cluster_kernel<<<B * CC_CL, CC_THREADS, 0, stream>>>(args, dptr);
     return cudaGetLastError();

@@ -222,10 +222,10 @@ extern "C" int vdd_create(const vdd_config* cfg, vdd_engine** out) {
   e->use_skinny = getenv("VDD_SKINNY") != nullptr;
   e->use_fused = getenv("VDD_NO_FUSED") == nullptr;
   // Whole-step persistent kernel (decode_step.cu) vs one gemv_kernel chain + one attention launch per layer (decode_gemv.cu):
-  // measured on one GPU the per-layer launches stream faster (cp.async rings: 6.7 TB/s inside a projection against 5.7 TB/s
-  // for 4 KB TMA tiles at the same 128 KB in flight per SM), under tensor parallelism the single launch wins (the step is a
-  // chain of latencies there, not a stream).  VDD_STEP=1 / 0 overrides.
-  e->use_step = getenv("VDD_STEP") ? atoi(getenv("VDD_STEP")) != 0 : tp > 1;
+  // measured (profiles/r2_step_kernel.md): the single launch streams the weights at HBM speed inside a projection, but its phase
+  // boundaries (8 warps of 255 registers for prologue / epilogue / attention) cost more than the launches they replace --
+  // 100 us per layer against 90 us on one GPU, 930 ms against 666 ms per 256-token generate at TP=2.  Opt-in: VDD_STEP=1.
+  e->use_step = getenv("VDD_STEP") ? atoi(getenv("VDD_STEP")) != 0 : false;
   if (getenv("VDD_TRACE")) {
     cudaMalloc(&e->d_trace, (size_t)256 * 64 * 8 * 8);
     cudaMemset(e->d_trace, 0, (size_t)256 * 64 * 8 * 8);
@@ -697,7 +697,8 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   if ((R > 8 || stream_small) && !getenv("VDD_ATTN_LEGACY")) {
     // measured on B200 (config 3, 96 rows, ms per decode step): 64-token kernel 8.51; chunk 128: 9.14, 512: 7.85, 1024: 7.40 --
     // one CTA per (row, head) up to 1024 tokens beats finer splits + merges even though main rows are 7x the debias rows
-    int chunk = getenv("VDD_ATTN_CHUNK") ? atoi(getenv("VDD_ATTN_CHUNK")) : (R > 8 ? 1024 : 128);
+    // under tensor parallelism a rank holds 1/tp of the heads: keep the CTA count (and the per-CTA serial KV stream) by splitting finer
+    int chunk = getenv("VDD_ATTN_CHUNK") ? atoi(getenv("VDD_ATTN_CHUNK")) : (R > 8 ? std::max(256, 1024 / c.tp_size) : 128);
     if (chunk < 64 || chunk % 64) chunk = 1024;
     for (int q = 0; q < R; ++q)
       for (int sp = 0; sp * chunk < kv_cap[q]; ++sp) { item_row.push_back(q); item_split.push_back(sp); }

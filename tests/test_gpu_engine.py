@@ -260,7 +260,7 @@ def test_many_rows_stream_k_chain_against_oracle(monkeypatch, B, use_none):
 def test_whole_step_kernel_against_oracle(monkeypatch, B, use_unk, use_none):
     """The opt-in whole-step persistent kernel (VDD_STEP=1, decode_step.cu: TMA-fed weight rings across all phases of a decode
     step, attention as a phase of the same launch) for 3 / 2 / 4 / 1 fused rows: teacher-forced stream logits against the
-    oracle, and its greedy tokens against the default per-layer launches."""
+    oracle, and its greedy VDD tokens against the oracle's (exact, or a near-tie of the oracle's own pre-warp scores)."""
     from llava_align_b200.model import LlavaLlamaForCausalLM, evolve_vcd_sampling
     cfg, sd, oracle = tiny_model(META["weight_seed"])
     evolve_vcd_sampling()
@@ -287,10 +287,5 @@ def test_whole_step_kernel_against_oracle(monkeypatch, B, use_unk, use_none):
               eos_token_id=None)
     out = m.generate(ids, **kw)
     assert eng.launch_count(reset=True) > 0
-    base = LlavaLlamaForCausalLM(cfg, "cuda:0")
-    base.load_state_dict(sd)
-    out2 = base.generate(ids, **kw)
     from helpers import greedy_divergence_is_near_tie
-    greedy_divergence_is_near_tie(out[:, T:].cpu(), out2[:, T:].cpu(), ref.stream_logits, 1.0, 0.1, 0.3) if (use_unk or use_none) else None
-    if not (use_unk or use_none):
-        assert torch.equal(out, out2) or True  # plain sampling rows: covered by the logits above
+    greedy_divergence_is_near_tie(out[:, T:].cpu(), ref.sequences[:, T:], ref.stream_logits, 1.0, 0.1, 0.3)

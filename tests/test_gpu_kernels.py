@@ -49,7 +49,8 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("V,B", [(32000, 4), (512, 3), (1000, 2)])
+# B < 96: one 8-CTA cluster (or one sorting CTA) per row;  B >= 96 without top-k / top-p ordering: the row-streaming persistent kernel
+@pytest.mark.parametrize("V,B", [(32000, 4), (512, 3), (1000, 2), (32000, 9), (1000, 12), (32000, 200)])
 @pytest.mark.parametrize("case", CASES)
 def test_combine_sample_matches_oracle(case, V, B):
     from llava_align_b200.engine import logit_combine_sample
@@ -85,6 +86,28 @@ def test_combine_sample_argmax_and_eos():
     exp_unf[0] = int(exp[0] != eos)
     exp_unf[3] = int(exp[3] != eos)
     assert torch.equal(unf.cpu(), exp_unf)
+
+
+def test_combine_sample_rows_kernel_eos_and_ties():
+    """Row-streaming kernel (B >= 96): EOS / pad bookkeeping, exact ties under top_k = 1 resolved by the race, no-q arg-max."""
+    from llava_align_b200.engine import logit_combine_sample
+    B, V = 128, 32000
+    l, u, d, q = _logit_case(B, V, 11)
+    l[3, 100] = l[3, 2000] = l[3].max() + 1.0  # an exact tie of the raw maximum; u = d = l there so the combined scores tie too
+    u[3, 100] = u[3, 2000] = d[3, 100] = d[3, 2000] = l[3, 100]
+    for qq in (q, None):
+        tok_ref, s_ref = O.vdd_step(l, u, d, 1.0, 0.1, None, 1, None, qq if qq is not None else torch.ones(B, V))
+        unf = torch.ones(B, dtype=torch.int32, device="cuda")
+        unf[[1, 7]] = 0
+        eos = int(tok_ref[2])
+        tok, s = logit_combine_sample(l.cuda(), u.cuda(), d.cuda(), 1.0, 0.1, None, 1, None, q=qq.cuda() if qq is not None else None,
+                                      want_scores=True, unfinished=unf, eos_token_id=eos, pad_token_id=0)
+        exp = tok_ref.clone()
+        exp[[1, 7]] = 0
+        assert torch.equal(tok.cpu(), exp)
+        assert torch.equal(torch.isinf(s.cpu()), torch.isinf(s_ref)) and int(torch.isfinite(s_ref[3]).sum()) == 2
+        exp_unf = torch.tensor([int(i not in (1, 7) and int(exp[i]) != eos) for i in range(B)], dtype=torch.int32)
+        assert torch.equal(unf.cpu(), exp_unf)
 
 
 def test_combine_sample_ties_split_by_top_p():
