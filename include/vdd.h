@@ -180,6 +180,16 @@ VDD_API int vdd_skinny_layer_chain(const void* attn_bf16, float* resid, const vo
  * 8+2q / 9+2q first stage landed / last MMA issued of projection q. */
 VDD_API int vdd_skinny_gemm_trace(unsigned long long* dev_buf);
 
+/* ---- host-side pipeline of the callers on the GPU -----------------------------------------------
+ * CLIP preprocessing of ONE image, replacing `image_processor.preprocess(image, return_tensors='pt')['pixel_values'][0]`
+ * (reference experiments/eval/sampling/llava_sampling.py:82, eval/calibrate/llava_calibrate.py:149; transformers-4.31
+ * CLIPImageProcessor + Pillow BICUBIC) and, with pad_rgb != NULL, the expand2square padding of reference
+ * experiments/llava/mm_utils.py:152-164 (pad_rgb = tuple(int(x * 255) for x in image_mean)).
+ *   rgb        uint8 [H, W, 3], host memory (copied inside) or device memory (rgb_on_device != 0)
+ *   out_dev    device [3, size, size]; out_dtype 0 = fp32 (bit-exact with the CPU pipeline), 1 = bf16, 2 = fp16            */
+VDD_API int vdd_clip_preprocess(const uint8_t* rgb, int H, int W, int rgb_on_device, int size, const uint8_t* pad_rgb,
+                        const float* mean3, const float* std3, void* out_dev, int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

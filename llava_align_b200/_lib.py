@@ -69,6 +69,7 @@ SIGNATURES = {
     "vdd_skinny_gemm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64, _P]),
     "vdd_skinny_gemm_trace": (C.c_int, [_P]),
     "vdd_skinny_layer_chain": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
+    "vdd_clip_preprocess": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
     "vdd_gemm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int64, _P]),
 }
 

@@ -47,6 +47,9 @@ def load_pretrained_model(model_path, model_base=None, model_name=None, load_8bi
         seed = int(parts[2]) if len(parts) > 2 else 0
         model = LlavaLlamaForCausalLM(cfg, dev, tp_size, tp_rank)
         _load_random(model, seed, exact=cfg.name == "tiny")
+        from .hostside import GpuClipImageProcessor
+        image_processor = GpuClipImageProcessor(cfg.image_size, device=dev)  # no HF files to read a processor config from
+        model.get_vision_tower().image_processor = image_processor
     else:
         # local checkpoint directory (reference builder.py:97-103,137-141): LLaVA shards + the CLIP tower they point at
         from .checkpoint import config_from_hf, iter_checkpoint_tensors

@@ -1591,6 +1591,16 @@ extern "C" int vdd_skinny_gemm_trace(unsigned long long* dev_buf) {
   g_sk_trace = dev_buf;
   return VDD_OK;
 }
+extern "C" int vdd_clip_preprocess(const uint8_t* rgb, int H, int W, int rgb_on_device, int size, const uint8_t* pad_rgb, const float* mean3,
+                                   const float* std3, void* out_dev, int out_dtype, void* stream_v) {
+  if (!rgb || !mean3 || !std3 || !out_dev) return fail(VDD_ERR_ARG, "null argument");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+    return fail(VDD_ERR_CUDA, "libvdd needs a CUDA device (sm_100a); none visible");
+  cudaError_t ce = launch_clip_preprocess(rgb, H, W, rgb_on_device != 0, size, pad_rgb, mean3, std3, out_dev, out_dtype, (cudaStream_t)stream_v);
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "clip_preprocess %dx%d -> %d: %s", H, W, size, cudaGetErrorString(ce));
+  return VDD_OK;
+}
 extern "C" int vdd_gemm(const void* a, const void* w, int M, int N, int K, int epilogue, const void* bias, const int32_t* row_map,
                         float* out_f32, void* out_bf16, int64_t ldc, void* stream_v) {
   GemmArgs g{a, w, M, N, K, epilogue, bias, row_map, out_f32, out_bf16, ldc};

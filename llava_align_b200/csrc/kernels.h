@@ -268,4 +268,10 @@ cudaError_t launch_scale_rows_bf16(const float* x, const void* g_bf16, void* out
 cudaError_t launch_cast_rows_bf16(const float* src, void* dst_bf16, int rows, int H, const int32_t* row_idx,
                                   cudaStream_t stream);
 
+// ---------------------------------------------------------------- CLIP image preprocessing (preprocess.cu)
+// uint8 RGB [H, W, 3] (host or device) -> [3, S, S] fp32 / bf16 / fp16 (out_dtype 0 / 1 / 2): optional square padding with pad_rgb,
+// Pillow-exact bicubic shortest-edge resize, center crop, * 1/255, (x - mean) / std
+cudaError_t launch_clip_preprocess(const uint8_t* rgb, int H, int W, bool on_device, int S, const uint8_t* pad_rgb, const float* mean,
+                                   const float* stdv, void* out, int out_dtype, cudaStream_t st);
+
 }  // namespace vdd

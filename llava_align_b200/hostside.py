@@ -102,12 +102,70 @@ def expand2square(pil_img, background_color):
     return canvas
 
 
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+class GpuClipImageProcessor:
+    """`image_processor` of the drivers, on the GPU: `preprocess(image, return_tensors='pt')['pixel_values'][0]` (reference
+    llava_sampling.py:82, llava_calibrate.py:149) returns the same float32 values as the transformers-4.31 CLIPImageProcessor the
+    reference loads (builder.py:137-141) -- Pillow BICUBIC shortest-edge resize, center crop, 1/255, CLIP mean / std -- computed
+    by libvdd (csrc/preprocess.cu) and left on the device (the drivers' `.half().cuda()` is then a device-side cast).
+    There is no CPU path: without the CUDA library this raises."""
+
+    def __init__(self, size=336, image_mean=CLIP_MEAN, image_std=CLIP_STD, device=None):
+        self.size = {"shortest_edge": int(size)}
+        self.crop_size = {"height": int(size), "width": int(size)}
+        self.image_mean, self.image_std = list(image_mean), list(image_std)
+        self.device = device
+
+    def _one(self, image, pad):
+        import ctypes as C
+        import numpy as np
+        from . import _lib
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.VddError("GpuClipImageProcessor needs a CUDA device (sm_100a); there is no CPU path")
+        dev = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+        if isinstance(image, torch.Tensor):
+            arr = image
+        else:
+            if hasattr(image, "convert"):
+                image = image.convert("RGB")  # do_convert_rgb
+            arr = torch.from_numpy(np.ascontiguousarray(np.asarray(image)))
+        if arr.dtype != torch.uint8 or arr.dim() != 3 or arr.shape[2] != 3:
+            raise ValueError(f"expected a uint8 RGB image [H, W, 3], got {tuple(arr.shape)} {arr.dtype}")
+        arr = arr.contiguous()
+        H, W = int(arr.shape[0]), int(arr.shape[1])
+        S = self.size["shortest_edge"]
+        out = torch.empty(3, S, S, dtype=torch.float32, device=dev)
+        mean = (C.c_float * 3)(*self.image_mean)
+        std = (C.c_float * 3)(*self.image_std)
+        bg = (C.c_uint8 * 3)(*[int(x * 255) for x in self.image_mean]) if pad else None  # mm_utils.py:171
+        with torch.cuda.device(dev):
+            _lib.check(lib.vdd_clip_preprocess(C.c_void_p(arr.data_ptr()), H, W, int(arr.is_cuda), S, bg, mean, std,
+                                               C.c_void_p(out.data_ptr()), 0, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                       "vdd_clip_preprocess")
+            if not arr.is_cuda:
+                torch.cuda.current_stream(dev).synchronize()  # the host pixels are read asynchronously
+        return out
+
+    def preprocess(self, images, return_tensors="pt", pad_to_square=False, **kwargs):
+        many = isinstance(images, (list, tuple))
+        outs = [self._one(im, pad_to_square) for im in (images if many else [images])]
+        return {"pixel_values": torch.stack(outs, dim=0)}
+
+    __call__ = preprocess
+
+
 def process_images(images, image_processor, model_cfg):
     mode = getattr(model_cfg, "image_aspect_ratio", None)
     if mode == "anyres":
         raise NotImplementedError("anyres multi-crop inputs are LLaVA-1.6; the VDD path is one 336px image per prompt")
     if mode != "pad":
         return image_processor(images, return_tensors="pt")["pixel_values"]
+    if isinstance(image_processor, GpuClipImageProcessor):  # the padding is folded into the resize kernel's source fetch
+        return image_processor.preprocess(list(images), return_tensors="pt", pad_to_square=True)["pixel_values"]
     bg = tuple(int(x * 255) for x in image_processor.image_mean)
     out = [image_processor.preprocess(expand2square(im, bg), return_tensors="pt")["pixel_values"][0] for im in images]
     return torch.stack(out, dim=0) if all(o.shape == out[0].shape for o in out) else out
@@ -173,7 +231,7 @@ def register_fallback_modules(pkg: str = "llava"):
         "constants": ("IGNORE_INDEX", "IMAGE_TOKEN_INDEX", "DEFAULT_IMAGE_TOKEN", "DEFAULT_IMAGE_PATCH_TOKEN",
                       "DEFAULT_IM_START_TOKEN", "DEFAULT_IM_END_TOKEN"),
         "mm_utils": ("tokenizer_image_token", "get_model_name_from_path", "KeywordsStoppingCriteria", "expand2square",
-                     "process_images"),
+                     "process_images", "GpuClipImageProcessor"),
         "utils": ("disable_torch_init",),
         "conversation": ("conv_templates", "SeparatorStyle", "Conversation"),
     }

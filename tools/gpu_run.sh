@@ -1,7 +1,6 @@
-timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "combine" > gpurun_out/r2i_k8_tests.log 2>&1; echo "k8 tests rc=$?"; tail -3 gpurun_out/r2i_k8_tests.log | head -2
-timeout 600 python -m pytest tests/test_gpu_engine.py -m gpu -q -k "whole_step" > gpurun_out/r2i_step_tests.log 2>&1; echo "step tests rc=$?"; tail -3 gpurun_out/r2i_step_tests.log | head -2
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
-timeout 400 $TR bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2i_tp2.json 2> gpurun_out/r2i_tp2.err; echo "tp2 rc=$?"; grep headline gpurun_out/r2i_tp2.err | head -1
-timeout 400 $TR bench.py --gpus 2 --steps 3 --warmup 2 --batch 32 --prompt-len 64 --new-tokens 64 --no-cpu-baseline > gpurun_out/r2i_tp2_cfg3_fused.json 2> gpurun_out/r2i_tp2_cfg3_fused.err; echo "tp2 cfg3 fused rc=$?"; grep headline gpurun_out/r2i_tp2_cfg3_fused.err | head -1
-VDD_TP_MANY_NCCL=1 timeout 400 $TR bench.py --gpus 2 --steps 3 --warmup 2 --batch 32 --prompt-len 64 --new-tokens 64 --no-cpu-baseline > gpurun_out/r2i_tp2_cfg3_nccl.json 2> gpurun_out/r2i_tp2_cfg3_nccl.err; echo "tp2 cfg3 nccl rc=$?"; grep headline gpurun_out/r2i_tp2_cfg3_nccl.err | head -1
-timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2i_n1.json 2> gpurun_out/r2i_n1.err; echo "n1 rc=$?"; grep -E "headline|configs" gpurun_out/r2i_n1.err
+# 4-GPU session: TP=4 parity at real width, 7B headline at TP=4, BASELINE configs[3] (13B, batch 8, use_dd_unk, TP=4)
+timeout 900 python -m pytest tests/test_tp_gpu.py -m gpu -q -k "real_width and 4-" > gpurun_out/r2j_tp4_tests.log 2>&1; echo "tp4 tests rc=$?"; tail -3 gpurun_out/r2j_tp4_tests.log | head -2
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511"
+timeout 400 $TR bench.py --gpus 4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2j_tp4.json 2> gpurun_out/r2j_tp4.err; echo "tp4 rc=$?"; grep headline gpurun_out/r2j_tp4.err | head -1
+timeout 600 $TR bench.py --gpus 4 --steps 3 --warmup 2 --model llava-v1.5-13b --batch 8 --flags unk --no-cpu-baseline > gpurun_out/r2j_cfg3_13b_b8_tp4.json 2> gpurun_out/r2j_cfg3_13b_b8_tp4.err; echo "cfg3 rc=$?"; grep headline gpurun_out/r2j_cfg3_13b_b8_tp4.err | head -1
+tail -3 gpurun_out/r2j_cfg3_13b_b8_tp4.err
