@@ -162,24 +162,6 @@ VDD_API int vdd_gemv(const void* w_bf16, const void* x_bf16, const float* x_f32_
 VDD_API int vdd_gemm(const void* a_bf16, const void* w_bf16, int M, int N, int K, int epilogue, const void* bias_bf16,
              const int32_t* row_map, float* out_f32, void* out_bf16, int64_t ldc, void* stream);
 
-/* Decode projection for 8 < R <= 256 fused rows (stream-K tcgen05 kernel, weights as the UMMA A operand):
- * out[r, n] = sum_k x[r, k] * w[n, k]; epilogue 0 = store fp32, 1 = += fp32, 5 = SwiGLU over interleaved gate/up -> bf16 [R, N/2]. */
-VDD_API int vdd_skinny_gemm(const void* w_bf16, const void* x_bf16, int R, int N, int K, int epilogue, float* out_f32,
-                    void* out_bf16, int64_t ld, void* stream);
-/* One decoder layer's projection chain for 8 < R <= 256 rows in ONE launch (what the engine issues per layer and step):
- *   resid += attn . Wo^T;  h = SwiGLU(rmsnorm(resid; g2) . Wgu^T);  resid += h . Wdown^T;  out = rmsnorm(resid; g3) . Wnext^T
- * replacing o_proj / post_attention_layernorm / gate_proj, up_proj / down_proj / the next input_layernorm + q,k,v_proj (or
- * norm + lm_head) of HF LlamaDecoderLayer as entered from reference llava_llama.py:91-103.  Wgu rows interleave gate/up;
- * xg [R,H] bf16 and h [R,I] bf16 are caller scratch. */
-VDD_API int vdd_skinny_layer_chain(const void* attn_bf16, float* resid, const void* wo_bf16, const void* g2_bf16, const void* wgu_bf16,
-                           const void* wdown_bf16, const void* g3_bf16, const void* wnext_bf16, int R, int H, int Hl, int I,
-                           int Nnext, float eps, void* xg_bf16, void* h_bf16, float* out_f32, void* stream);
-/* Debug: per-CTA %globaltimer stamps of the next vdd_skinny_gemm launches into dev_buf [148][16] u64 (NULL disarms):
- * 0 entry, 1 first weights requested, 2 previous kernel complete, 3 first stage landed, 4 last MMA issued,
- * 5 first projection drained, 6 its fix-up done (arriving at the grid barrier), 7 that barrier observed by the producer,
- * 8+2q / 9+2q first stage landed / last MMA issued of projection q. */
-VDD_API int vdd_skinny_gemm_trace(unsigned long long* dev_buf);
-
 /* ---- host-side pipeline of the callers on the GPU -----------------------------------------------
  * CLIP preprocessing of ONE image, replacing `image_processor.preprocess(image, return_tensors='pt')['pixel_values'][0]`
  * (reference experiments/eval/sampling/llava_sampling.py:82, eval/calibrate/llava_calibrate.py:149; transformers-4.31

@@ -66,9 +66,6 @@ SIGNATURES = {
     "vdd_bench_projection_chain": (C.c_int, [_P, _P]),
     "vdd_debug_trace": (C.c_int, [_P, _P, C.c_int]),
     "vdd_gemv": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
-    "vdd_skinny_gemm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int64, _P]),
-    "vdd_skinny_gemm_trace": (C.c_int, [_P]),
-    "vdd_skinny_layer_chain": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
     "vdd_clip_preprocess": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
     "vdd_gemm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int64, _P]),
 }

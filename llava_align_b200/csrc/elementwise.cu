@@ -139,25 +139,6 @@ cudaError_t launch_reduce_rmsnorm(float* resid, const float* ws, int splits, int
                             (__nv_bfloat16*)out, H, wait, wait_per_epoch, epoch);
 }
 
-// B operand of a row-scaled projection (decode_gemm.cu): out = bf16(x * g); the 1/rms factor is applied by the consumer.
-__global__ void __launch_bounds__(256) scale_rows_bf16_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ g,
-                                                             __nv_bfloat16* __restrict__ out, int H) {
-  const float* xr = x + (size_t)blockIdx.x * H;
-  for (int k = threadIdx.x * 4; k < H; k += 256 * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + k);
-    const uint2 wv = *reinterpret_cast<const uint2*>(g + k);
-    uint2 o;
-    o.x = pack_bf16(v.x * bf16lo(wv.x), v.y * bf16hi(wv.x));
-    o.y = pack_bf16(v.z * bf16lo(wv.y), v.w * bf16hi(wv.y));
-    *reinterpret_cast<uint2*>(out + (size_t)blockIdx.x * H + k) = o;
-  }
-}
-cudaError_t launch_scale_rows_bf16(const float* x, const void* g, void* out, int rows, int H, cudaStream_t stream) {
-  if (rows <= 0) return cudaSuccess;
-  scale_rows_bf16_kernel<<<rows, 256, 0, stream>>>(x, (const __nv_bfloat16*)g, (__nv_bfloat16*)out, H);
-  return cudaGetLastError();
-}
-
 // ------------------------------------------------------------------------------------------------ LayerNorm (CLIP)
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                                        const __nv_bfloat16* __restrict__ b, float eps,

@@ -98,9 +98,7 @@ struct vdd_engine {
   vdd_config c;
   int D = 128, heads_l = 0, Hl = 0, Il = 0, Vl = 0, NP = 0, Kpad = 0, VD = 64;
   int num_sms = 148;
-  bool use_pdl = true, use_graph = true, use_fused = true, use_skinny = true;
-  int* sk_counters = nullptr;  // per decode step: one zeroed block per skinny-chain launch (SK_BLOCK_INTS)
-  float* sk_inv_rms = nullptr; // [launch][4][256] row scales
+  bool use_pdl = true, use_graph = true, use_fused = true;
   // weights
   void* arena = nullptr;
   size_t arena_bytes = 0;
@@ -112,7 +110,7 @@ struct vdd_engine {
   void *patch_w, *cls, *vpos, *preln_w, *preln_b, *pj_w1, *pj_b1, *pj_w2, *pj_b2;
   float *rope_cos = nullptr, *rope_sin = nullptr;
   // workspaces
-  DevBuf resid, xn, qkv, qb, attn, hbuf, meta, kv, logits, logits_tp, dec_f32, dec_bf16, part, img_feats, vis, pix, misc, tp_tmp, split_ws, sk_ws, sk_cnt;
+  DevBuf resid, xn, qkv, qb, attn, hbuf, meta, kv, logits, logits_tp, dec_f32, dec_bf16, part, img_feats, vis, pix, misc, tp_tmp, split_ws;
   // per-generation plan
   int B = 0, T = 0, S = 0, R = 0, Mtot = 0, max_new = 0, max_len = 0, max_splits = 1;
   int attn_items = 0, attn_chunk = 0;  // streaming decode attention (R > 8): (row, split) work table
@@ -217,9 +215,6 @@ extern "C" int vdd_create(const vdd_config* cfg, vdd_engine** out) {
   cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev);
   e->use_pdl = getenv("VDD_NO_PDL") == nullptr;
   e->use_graph = getenv("VDD_NO_GRAPH") == nullptr;
-  // Stand-alone stream-K launches lose to the square-tile GEMM + split-K at R = 96 (per-launch set-up, first fill, drain and
-  // the shared-tile fix-up cost ~14 us against a 15 us stream: profiles/r1_trace_skinny.json); opt-in until chained.
-  e->use_skinny = getenv("VDD_SKINNY") != nullptr;
   e->use_fused = getenv("VDD_NO_FUSED") == nullptr;
   // Whole-step persistent kernel (decode_step.cu) vs one gemv_kernel chain + one attention launch per layer (decode_gemv.cu):
   // measured (profiles/r2_step_kernel.md): the single launch streams the weights at HBM speed inside a projection, but its phase
@@ -343,8 +338,7 @@ extern "C" void vdd_destroy(vdd_engine* e) {
   cudaDeviceSynchronize();
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   DevBuf* bufs[] = {&e->resid, &e->xn, &e->qkv, &e->qb, &e->attn, &e->hbuf, &e->meta, &e->kv, &e->logits, &e->logits_tp,
-                    &e->dec_f32, &e->dec_bf16, &e->part, &e->img_feats, &e->vis, &e->pix, &e->misc, &e->tp_tmp, &e->split_ws, &e->sk_ws, &e->sk_cnt,
-                    &e->step_tab};
+                    &e->dec_f32, &e->dec_bf16, &e->part, &e->img_feats, &e->vis, &e->pix, &e->misc, &e->tp_tmp, &e->split_ws, &e->step_tab};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (e->arena) cudaFree(e->arena);
@@ -466,6 +460,11 @@ static int do_gemm(vdd_engine* e, const void* a, const void* w, int M, int N, in
     return fail(VDD_ERR_CUDA, "gemm M=%d N=%d K=%d: %s %s", M, N, K, cudaGetErrorString(ce), gemm_init_error() ? gemm_init_error() : "");
   return VDD_OK;
 }
+static bool tp_push_pays(int R, int tp) {
+  if (getenv("VDD_TP_MANY_NCCL")) return false;
+  if (getenv("VDD_TP_MANY_PUSH")) return true;
+  return R * tp <= 256;
+}
 // Row-parallel / vocab-parallel projection under tensor parallelism, many-row decode path: the tcgen05 GEMM's epilogue stores its
 // tiles into every rank's peer-visible buffer at byte offset `dst_off` (plus nothing else: the caller folds rank / slot / column
 // offsets into it) and every CTA bumps arrival counter `counter` on every rank.  *nctas = CTAs of the launch.
@@ -483,37 +482,6 @@ static int gemm_tp_push(vdd_engine* e, const void* x, const void* w, int M, int 
   e->launches++;
   if (ce != cudaSuccess)
     return fail(VDD_ERR_CUDA, "tp gemm M=%d N=%d K=%d: %s %s", M, N, K, cudaGetErrorString(ce), gemm_init_error() ? gemm_init_error() : "");
-  return VDD_OK;
-}
-// Zero-on-entry state of the skinny-GEMM chain launches of ONE decode step (cleared by a single memset per step):
-// launch li (0 = first layer's qkv, 1 + l = chain of layer l) owns a block of SK_BLOCK_INTS ints:
-//   [0, 4*SK_CNT_STRIDE)  tile counters of its (up to) four projections
-//   [.., +4)              grid barriers        [.., +4) row-statistic counters
-constexpr int SK_CNT_STRIDE = 256;  // >= N/256 tiles of any projection
-constexpr int SK_BLOCK_INTS = 4 * SK_CNT_STRIDE + 8;
-static SkinnyArgs sk_args(const void* x, const void* w, int N, int K, int mode, float* of32, void* obf16, int64_t ld, int64_t ld_bf16) {
-  SkinnyArgs a{};
-  a.w = w; a.x = x; a.N = N; a.K = K; a.epilogue = mode; a.out_f32 = of32; a.out_bf16 = obf16; a.ld = ld; a.ld_bf16 = ld_bf16;
-  return a;
-}
-// chain launch number `li` of the current decode step: wires the zeroed counters / barriers / scratch of its block
-static int do_skinny_chain(vdd_engine* e, SkinnyChain& ch, int li, cudaStream_t st) {
-  int* blk = e->sk_counters + (size_t)li * SK_BLOCK_INTS;
-  for (int q = 0; q < ch.n; ++q) {
-    if (skinny_gemm_tiles(ch.ph[q].N) > SK_CNT_STRIDE) return fail(VDD_ERR_UNSUPPORTED, "skinny gemm: N=%d too wide", ch.ph[q].N);
-    ch.ph[q].counters = blk + q * SK_CNT_STRIDE;
-    if (ch.ph[q].rs_x) {
-      ch.ph[q].norm_counter = blk + 4 * SK_CNT_STRIDE + 4 + q;
-      ch.ph[q].inv_rms = e->sk_inv_rms + ((size_t)li * 4 + q) * 256;
-    }
-  }
-  ch.R = e->R;
-  ch.ws = (float*)e->sk_ws.p;
-  ch.ws_bytes = e->sk_ws.bytes;
-  ch.barrier = (unsigned*)(blk + 4 * SK_CNT_STRIDE);
-  cudaError_t ce = launch_skinny_chain(ch, e->num_sms, e->use_pdl, st);
-  e->launches++;
-  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny chain (R=%d, %d projections): %s", e->R, ch.n, cudaGetErrorString(ce));
   return VDD_OK;
 }
 #define RC(x)               \
@@ -717,17 +685,6 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   RC(ensure(e, e->kv, (size_t)2 * L * kv_total * 2));
   RC(ensure(e, e->logits, (size_t)R * c.vocab_size * 4));
   if (R > 8 && R <= 128) RC(ensure(e, e->split_ws, (size_t)8 * R * H * 4));
-  e->sk_counters = nullptr;
-  if (R > 8 && R <= 256 && e->use_skinny && c.tp_size == 1) {
-    size_t ws = 0;
-    const int shapes[5][2] = {{3 * Hl, H}, {H, Hl}, {2 * Il, H}, {H, Il}, {e->Vl, H}};
-    for (auto& sh : shapes) ws = std::max(ws, skinny_gemm_ws_bytes(R, sh[0], sh[1], e->num_sms));
-    RC(ensure(e, e->sk_ws, ws));
-    const size_t cnt_bytes = align_up((size_t)(L + 1) * SK_BLOCK_INTS * 4, 256);
-    RC(ensure(e, e->sk_cnt, cnt_bytes + (size_t)(L + 1) * 4 * 256 * 4));
-    e->sk_counters = (int*)e->sk_cnt.p;
-    e->sk_inv_rms = (float*)((char*)e->sk_cnt.p + cnt_bytes);
-  }
   if (c.tp_size > 1) {
     RC(ensure(e, e->logits_tp, (size_t)R * c.vocab_size * 4));
     RC(ensure(e, e->tp_tmp, (size_t)(Mtot > R ? Mtot : R) * H * 4));
@@ -981,29 +938,20 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     if (!projections_only) e->logits_cur = tpf ? (float*)((char*)e->comm_buf + e->tpc.off_logits) : (float*)e->logits.p;
     return VDD_OK;
   }
-  // 8 < R <= 256 on one GPU: stream-K tcgen05 chain, one launch per layer (decode_gemm.cu), RMSNorm folded into the epilogues
-  const bool skinny = R > 8 && R <= 256 && e->use_skinny && e->sk_counters && !tp;
-  if (skinny) CK(cudaMemsetAsync(e->sk_counters, 0, (size_t)(L + 1) * SK_BLOCK_INTS * 4, st));
   auto gemm = [&](const void* x, const void* w, int N, int K, int mode, float* of32, void* obf16, int64_t ld) -> int {
     return do_gemm(e, x, w, R, N, K, mode, nullptr, nullptr, of32, obf16, ld, st);
   };
   if (!projections_only) LK(e, launch_decode_embed(e->embed, tokens, e->resid_d, e->B, e->S, H, st));
   if (fused) LK(e, launch_gemv(qkv_args(0), e->num_sms, pdl, st));
-  if (skinny) {
-    // layer 0: qkv = (W (g .* resid)) / rms(resid); every later qkv rides at the end of the previous layer's chain
-    LK(e, launch_scale_rows_bf16(e->resid_d, e->lw[0].ln1, e->xn_d, R, H, st));
-    SkinnyChain ch{};
-    ch.n = 1;
-    ch.ph[0] = sk_args(e->xn_d, e->lw[0].wqkv, 3 * Hl, H, GEMM_OUT_F32, e->qkv_d, nullptr, 3 * Hl, 0);
-    ch.ph[0].rs_x = e->resid_d; ch.ph[0].rs_K = H; ch.ph[0].rs_eps = c.rms_eps;
-    RC(do_skinny_chain(e, ch, 0, st));
-  }
   // 8 < R on one GPU, square-tile GEMMs: every launch of the layer is programmatically serialised (set-up overlaps the
   // predecessor's tail), and the split-K reduction of o_proj / down_proj is folded into the RMSNorm pass that follows it
   // ... and under tensor parallelism with mapped peers: same launches, the all-reduce rides in the o_proj / down_proj epilogues
   // (peer stores + arrival counters) and in the reduce + RMSNorm pass that follows them; the logits are gathered the same way
-  const bool tpm = tp && tpf && R > 8 && R <= e->tp_max_rows && getenv("VDD_TP_MANY_NCCL") == nullptr;
-  const bool wide = R > 8 && !skinny && (!tp || tpm);
+  // Push-to-all costs tp x the message over NVLink and tp stores per accumulator in the epilogue: it wins while the message is
+  // small (configs[2] shape at TP=2: 6.48 vs 6.67 ms per step with NCCL launches; configs[3]: 16 rows at TP=4) and loses badly when
+  // it is not (configs[4]: 192 rows x 8 ranks = 31 MB per all-reduce, 23.2 ms per step against 11.4 ms with NCCL): rows x ranks <= 256.
+  const bool tpm = tp && tpf && R > 8 && R <= e->tp_max_rows && tp_push_pays(R, c.tp_size);
+  const bool wide = R > 8 && (!tp || tpm);
   const size_t slot_bytes = (size_t)c.tp_size * e->tp_max_rows * H * 4;   // one inbox slot on every rank
   const size_t plane_off = (size_t)c.tp_rank * R * H * 4;                 // this rank's plane inside a slot
   const float* inbox_local = tpm ? (const float*)((const char*)e->comm_buf + e->tpc.off_inbox) : nullptr;
@@ -1013,7 +961,7 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     const LayerW& w = e->lw[l];
     if (wide) {
       RC(do_gemm(e, e->xn_d, w.wqkv, R, 3 * Hl, H, GEMM_OUT_F32, nullptr, nullptr, e->qkv_d, nullptr, 3 * Hl, st, pdl));
-    } else if (!fused && !skinny) {
+    } else if (!fused) {
       if (R <= 8) {
         LK(e, launch_gemv(qkv_args(l), e->num_sms, pdl, st));
       } else {
@@ -1044,22 +992,6 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
       ch.barrier = e->d_bar + (size_t)l * 4;
       ch.trace = (l == L / 2) ? e->d_trace : nullptr;
       LK(e, launch_gemv_chain(ch, e->num_sms, pdl, st));
-      continue;
-    }
-    if (skinny) {
-      const bool last = l + 1 == L;
-      SkinnyChain ch{};
-      ch.n = 4;
-      ch.ph[0] = sk_args(e->attn_d, w.wo, H, Hl, GEMM_OUT_RESID_XG, e->resid_d, e->xn_d, H, H);
-      ch.ph[0].g = w.ln2;
-      ch.ph[1] = sk_args(e->xn_d, w.wgu, 2 * Il, H, GEMM_OUT_SWIGLU, nullptr, e->h_d, 0, Il);
-      ch.ph[1].rs_x = e->resid_d; ch.ph[1].rs_K = H; ch.ph[1].rs_eps = c.rms_eps;
-      ch.ph[2] = sk_args(e->h_d, w.wdown, H, Il, GEMM_OUT_RESID_XG, e->resid_d, e->xn_d, H, H);
-      ch.ph[2].g = last ? e->final_norm : e->lw[l + 1].ln1;
-      ch.ph[3] = last ? sk_args(e->xn_d, e->lm_head, e->Vl, H, GEMM_OUT_F32, lg, nullptr, e->Vl, 0)
-                      : sk_args(e->xn_d, e->lw[l + 1].wqkv, 3 * Hl, H, GEMM_OUT_F32, e->qkv_d, nullptr, 3 * Hl, 0);
-      ch.ph[3].rs_x = e->resid_d; ch.ph[3].rs_K = H; ch.ph[3].rs_eps = c.rms_eps;
-      RC(do_skinny_chain(e, ch, 1 + l, st));
       continue;
     }
     if (wide && tpm) {
@@ -1104,7 +1036,7 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     }
     if (tp) RC(tp_allreduce_add(e, o_dst, e->resid_d, (int64_t)R * H, st));
   }
-  if (!fused && !skinny) {
+  if (!fused) {
     if (R <= 8) {
       LK(e, launch_gemv(head_args(), e->num_sms, pdl, st));
     } else if (wide && tpm) {
@@ -1305,8 +1237,7 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
     CK(cudaMemcpyAsync(e->d_sargs, e->pinned, sizeof a, cudaMemcpyHostToDevice, st));
     RC(prepare_step(e, st));  // the phase table is per row count
   }
-  const bool tp_many = e->tp_fused_ready && e->R > 8 && e->R <= e->tp_max_rows && !(e->use_skinny && e->sk_counters) &&
-                       getenv("VDD_TP_MANY_NCCL") == nullptr;
+  const bool tp_many = e->tp_fused_ready && e->R > 8 && e->R <= e->tp_max_rows && tp_push_pays(e->R, c.tp_size);
   if (e->tp_fused_ready && ((e->R <= 8 && e->use_fused) || tp_many) && max_new > 1) {
     // decode steps leave their (all-gathered) logits in the peer-visible buffer: re-point the sampler there
     CK(cudaStreamSynchronize(st));
@@ -1328,11 +1259,11 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
     auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
     mix((uint64_t)B); mix((uint64_t)S); mix((uint64_t)e->R); mix((uint64_t)e->Mtot); mix((uint64_t)e->max_splits);
     mix((uint64_t)e->attn_items); mix((uint64_t)e->attn_chunk);
-    mix((uint64_t)(e->use_pdl ? 1 : 0) | (uint64_t)(e->use_fused ? 2 : 0) | (uint64_t)(e->tp_fused_ready ? 8 : 0) | (uint64_t)(e->use_skinny ? 16 : 0) |
+    mix((uint64_t)(e->use_pdl ? 1 : 0) | (uint64_t)(e->use_fused ? 2 : 0) | (uint64_t)(e->tp_fused_ready ? 8 : 0) |
         (uint64_t)((a.top_p < 1.0f || (a.top_k > 1 && a.top_k < V)) ? 4 : 0));  // bit 2: which K8 kernel the graph holds
     mix((uint64_t)(uintptr_t)e->kv.p); mix((uint64_t)(uintptr_t)e->logits.p); mix((uint64_t)e->kv_layer_stride);
     mix((uint64_t)(uintptr_t)e->meta.p); mix((uint64_t)(uintptr_t)e->dec_f32.p); mix((uint64_t)(uintptr_t)e->dec_bf16.p);
-    mix((uint64_t)(uintptr_t)e->sk_ws.p); mix((uint64_t)(uintptr_t)e->split_ws.p);
+    mix((uint64_t)(uintptr_t)e->split_ws.p);
     // the meta carve-out places the sampler arguments, barriers and work table BEHIND the [B, max_new] sequence buffer, so
     // their addresses move with max_new even when every shape above is unchanged
     mix((uint64_t)(e->step_ready ? 1 + e->step_launch.nw * 16 + e->step_launch.depth : 0)); mix((uint64_t)(uintptr_t)e->step_tab.p);
@@ -1513,82 +1444,6 @@ extern "C" int vdd_gemv(const void* w, const void* x_bf16, const float* x_resid,
   g.ld_out = epilogue == GEMV_OUT_SWIGLU_BF16 ? N / 2 : N;
   cudaError_t ce = launch_gemv(g, sms, getenv("VDD_NO_PDL") == nullptr, (cudaStream_t)stream_v);
   if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "gemv R=%d N=%d K=%d: %s", R, N, K, cudaGetErrorString(ce));
-  return VDD_OK;
-}
-static unsigned long long* g_sk_trace = nullptr;
-static float* g_sk_ws = nullptr;
-static size_t g_sk_ws_bytes = 0;
-static int* g_sk_cnt = nullptr;
-static int sk_test_scratch(size_t need) {
-  if (need > g_sk_ws_bytes) {
-    if (g_sk_ws) cudaFree(g_sk_ws);
-    g_sk_ws_bytes = 0;
-    if (cudaMalloc(&g_sk_ws, need) != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm scratch: out of memory");
-    g_sk_ws_bytes = need;
-  }
-  if (!g_sk_cnt && cudaMalloc(&g_sk_cnt, (SK_BLOCK_INTS + 4 * 256) * 4) != cudaSuccess)
-    return fail(VDD_ERR_CUDA, "skinny gemm counters: out of memory");
-  return VDD_OK;
-}
-extern "C" int vdd_skinny_gemm(const void* w, const void* x_bf16, int R, int N, int K, int epilogue, float* out_f32, void* out_bf16,
-                               int64_t ld, void* stream_v) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (skinny_gemm_tiles(N) > SK_CNT_STRIDE) return fail(VDD_ERR_UNSUPPORTED, "N too wide");
-  RC(sk_test_scratch(skinny_gemm_ws_bytes(R, N, K, sms)));
-  cudaStream_t st = (cudaStream_t)stream_v;
-  cudaMemsetAsync(g_sk_cnt, 0, SK_BLOCK_INTS * 4, st);
-  SkinnyChain ch{};
-  ch.R = R; ch.n = 1;
-  ch.ph[0] = sk_args(x_bf16, w, N, K, epilogue, out_f32, out_bf16, ld, ld);
-  ch.ph[0].counters = g_sk_cnt;
-  ch.ws = g_sk_ws; ch.ws_bytes = g_sk_ws_bytes; ch.barrier = nullptr; ch.trace = g_sk_trace;
-  cudaError_t ce = launch_skinny_chain(ch, sms, getenv("VDD_NO_PDL") == nullptr, st);
-  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny gemm R=%d N=%d K=%d: %s", R, N, K, cudaGetErrorString(ce));
-  return VDD_OK;
-}
-/* One decoder layer's projection chain for 8 < R <= 256 rows, stand-alone (tests / micro-benchmarks):
- *   resid += attn . Wo^T;  h = SwiGLU(rmsnorm(resid; g2) . Wgu^T);  resid += h . Wdown^T;  out = rmsnorm(resid; g3) . Wnext^T
- * xg [R,H] bf16 and h [R,I] bf16 are scratch.  Wgu rows interleave gate/up. */
-extern "C" int vdd_skinny_layer_chain(const void* attn_bf16, float* resid, const void* wo, const void* g2, const void* wgu, const void* wdown,
-                                      const void* g3, const void* wnext, int R, int H, int Hl, int I, int Nnext, float eps, void* xg_bf16,
-                                      void* h_bf16, float* out_f32, void* stream_v) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  size_t need = 0;
-  const int shapes[4][2] = {{H, Hl}, {2 * I, H}, {H, I}, {Nnext, H}};
-  for (auto& sh : shapes) {
-    if (skinny_gemm_tiles(sh[0]) > SK_CNT_STRIDE) return fail(VDD_ERR_UNSUPPORTED, "N too wide");
-    need = std::max(need, skinny_gemm_ws_bytes(R, sh[0], sh[1], sms));
-  }
-  RC(sk_test_scratch(need));
-  cudaStream_t st = (cudaStream_t)stream_v;
-  cudaMemsetAsync(g_sk_cnt, 0, SK_BLOCK_INTS * 4, st);
-  float* inv = (float*)(g_sk_cnt + SK_BLOCK_INTS);
-  SkinnyChain ch{};
-  ch.R = R; ch.n = 4;
-  ch.ph[0] = sk_args(attn_bf16, wo, H, Hl, GEMM_OUT_RESID_XG, resid, xg_bf16, H, H);
-  ch.ph[0].g = g2;
-  ch.ph[1] = sk_args(xg_bf16, wgu, 2 * I, H, GEMM_OUT_SWIGLU, nullptr, h_bf16, 0, I);
-  ch.ph[1].rs_x = resid; ch.ph[1].rs_K = H; ch.ph[1].rs_eps = eps;
-  ch.ph[2] = sk_args(h_bf16, wdown, H, I, GEMM_OUT_RESID_XG, resid, xg_bf16, H, H);
-  ch.ph[2].g = g3;
-  ch.ph[3] = sk_args(xg_bf16, wnext, Nnext, H, GEMM_OUT_F32, out_f32, nullptr, Nnext, 0);
-  ch.ph[3].rs_x = resid; ch.ph[3].rs_K = H; ch.ph[3].rs_eps = eps;
-  for (int q = 0; q < 4; ++q) {
-    ch.ph[q].counters = g_sk_cnt + q * SK_CNT_STRIDE;
-    if (ch.ph[q].rs_x) { ch.ph[q].norm_counter = g_sk_cnt + 4 * SK_CNT_STRIDE + 4 + q; ch.ph[q].inv_rms = inv + q * 256; }
-  }
-  ch.ws = g_sk_ws; ch.ws_bytes = g_sk_ws_bytes; ch.barrier = (unsigned*)(g_sk_cnt + 4 * SK_CNT_STRIDE); ch.trace = g_sk_trace;
-  cudaError_t ce = launch_skinny_chain(ch, sms, getenv("VDD_NO_PDL") == nullptr, st);
-  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "skinny layer chain R=%d: %s", R, cudaGetErrorString(ce));
-  return VDD_OK;
-}
-/* Debug: arm (device buffer of [grid][16] u64 globaltimer stamps) or disarm (NULL) tracing of vdd_skinny_gemm launches. */
-extern "C" int vdd_skinny_gemm_trace(unsigned long long* dev_buf) {
-  g_sk_trace = dev_buf;
   return VDD_OK;
 }
 extern "C" int vdd_clip_preprocess(const uint8_t* rgb, int H, int W, int rgb_on_device, int size, const uint8_t* pad_rgb, const float* mean3,

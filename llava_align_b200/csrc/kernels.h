@@ -124,8 +124,7 @@ enum GemmEpilogue {
   GEMM_OUT_BF16 = 2,       // out_bf16 = acc (+bias)
   GEMM_OUT_BF16_QGELU = 3, // quick_gelu(acc+bias)   (CLIP MLP)
   GEMM_OUT_BF16_GELU = 4,  // gelu_erf(acc+bias)     (mm_projector)
-  GEMM_OUT_SWIGLU = 5,     // out_bf16[row, col/2] = silu(acc[2i]) * acc[2i+1]  (interleaved gate/up)
-  GEMM_OUT_RESID_XG = 6    // skinny chain only: out_f32 += acc; out_bf16 = bf16(out_f32 * g[col])  (residual + next norm's operand)
+  GEMM_OUT_SWIGLU = 5      // out_bf16[row, col/2] = silu(acc[2i]) * acc[2i+1]  (interleaved gate/up)
 };
 struct GemmArgs {
   const void* a;  // bf16 [M, K] row-major (lda = K)
@@ -153,36 +152,6 @@ struct GemmArgs {
 };
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
 const char* gemm_init_error();
-
-// ---------------------------------------------------------------- tcgen05 skinny GEMM chain for decode (8 < R <= 256 rows)
-// One projection: out[r, n] (op)= sum_k x[r, k] * w[n, k], optionally scaled per row by 1/rms(rs_x[r, :]) (the RMSNorm of
-// the consumer, see decode_gemm.cu).  Up to four dependent projections run in one launch.
-struct SkinnyArgs {
-  const void* w;  // bf16 [N, K]
-  const void* x;  // bf16 [R, K]
-  int N, K, epilogue;  // GEMM_OUT_F32 | GEMM_OUT_ADD_F32 | GEMM_OUT_SWIGLU | GEMM_OUT_RESID_XG
-  float* out_f32;      // F32: store; ADD_F32 / RESID_XG: +=   (row pitch ld)
-  void* out_bf16;      // SWIGLU: [R, N/2]; RESID_XG: bf16((out_f32 after the add) * g)   (row pitch ld_bf16)
-  int64_t ld, ld_bf16;
-  const void* g = nullptr;        // RESID_XG: bf16 [N] weight of the next RMSNorm
-  const float* rs_x = nullptr;    // row scale source [R, rs_K] fp32, or null
-  int rs_K = 0;
-  float rs_eps = 0.f;
-  float* inv_rms = nullptr;       // [R] scratch
-  int* norm_counter = nullptr;    // zero on entry
-  int* counters = nullptr;        // [skinny_gemm_tiles(N)] zero on entry (left non-zero)
-};
-struct SkinnyChain {
-  int R, n;
-  SkinnyArgs ph[4];
-  float* ws;          // fp32 scratch for tiles shared by several CTAs: max over phases of skinny_gemm_ws_bytes
-  size_t ws_bytes;
-  unsigned* barrier;  // [n - 1] zero on entry
-  unsigned long long* trace = nullptr;  // debug: [grid][16] globaltimer stamps
-};
-cudaError_t launch_skinny_chain(const SkinnyChain& ch, int num_sms, bool pdl, cudaStream_t stream);
-size_t skinny_gemm_ws_bytes(int R, int N, int K, int num_sms);
-int skinny_gemm_tiles(int N);
 
 // ---------------------------------------------------------------- attention
 struct DecodeAttnArgs {
@@ -264,7 +233,6 @@ cudaError_t launch_decode_embed(const void* table_bf16, const int64_t* tokens, f
 cudaError_t launch_advance(int32_t* pos, int R, int32_t* step, cudaStream_t stream, int32_t* epoch = nullptr);  // pos[r] += 1, *step += 1, *epoch += 1
 cudaError_t launch_add_rows(float* dst, const float* src, int64_t n, cudaStream_t stream);
 cudaError_t launch_reduce_splits(float* dst, const float* ws, int64_t n, int splits, cudaStream_t stream);  // dst += sum_z ws[z]
-cudaError_t launch_scale_rows_bf16(const float* x, const void* g_bf16, void* out_bf16, int rows, int H, cudaStream_t stream);  // out = bf16(x * g)
 cudaError_t launch_cast_rows_bf16(const float* src, void* dst_bf16, int rows, int H, const int32_t* row_idx,
                                   cudaStream_t stream);
 

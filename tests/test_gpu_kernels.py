@@ -209,92 +209,3 @@ def test_gemm_epilogues(M, N, K):
     exp = torch.zeros(M, N, device="cuda")
     exp[rm[1:].long()] = ref[1:]
     torch.testing.assert_close(out, exp, **tol)
-
-
-# ------------------------------------------------------------------------------------------------ tcgen05 skinny (stream-K) decode GEMM
-@pytest.mark.parametrize("R", [9, 16, 33, 96, 130, 192, 256])
-@pytest.mark.parametrize("N,K", [(4096, 4096), (12288, 4096), (4096, 11008), (1000, 1376), (256, 64), (32000, 512)])
-def test_skinny_gemm_epilogues(R, N, K):
-    """Rows on both sides of the TMEM double-buffer switch (R <= 128 / > 128); N and K off the 256 / 64 tile; tiles owned
-    by one CTA and tiles shared by many (o_proj / down_proj shapes: 16 tiles over 148 SMs)."""
-    L = _lib()
-    lib = L.load()
-    g = torch.Generator(device="cuda").manual_seed(R * 7 + N + K)
-    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
-    x = torch.randn(R, K, device="cuda", generator=g).bfloat16()
-    ref = x.float() @ W.float().T
-    tol = dict(rtol=2e-3, atol=2e-3)
-    out = torch.full((R, N), 7.0, device="cuda")
-    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), R, N, K, 0, _ptr(out), None, N, _stream()), "skinny f32")
-    torch.testing.assert_close(out, ref, **tol)
-    out_b = torch.full((R, N), 7.0, device="cuda")
-    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), R, N, K, 0, _ptr(out_b), None, N, _stream()), "skinny f32 again")
-    assert torch.equal(out, out_b), "split tiles must reduce in a fixed order"
-    base = torch.randn(R, N, device="cuda", generator=g)
-    out2 = base.clone()
-    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), R, N, K, 1, _ptr(out2), None, N, _stream()), "skinny add")
-    torch.testing.assert_close(out2, base + ref, **tol)
-    oh = torch.zeros(R, N // 2, device="cuda", dtype=torch.bfloat16)
-    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), R, N, K, 5, None, _ptr(oh), N // 2, _stream()), "skinny swiglu")
-    torch.testing.assert_close(oh.float(), torch.nn.functional.silu(ref[:, 0::2]) * ref[:, 1::2], rtol=1e-2, atol=1e-2)
-
-
-def test_skinny_gemm_rows_do_not_depend_on_batch():
-    """A row's result is bit-identical whatever other rows share the launch (the stream-K cut depends on N, K and the grid only)."""
-    L = _lib()
-    lib = L.load()
-    N, K = 4096, 4096
-    g = torch.Generator(device="cuda").manual_seed(5)
-    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
-    x = torch.randn(96, K, device="cuda", generator=g).bfloat16()
-    o96 = torch.zeros(96, N, device="cuda")
-    o20 = torch.zeros(20, N, device="cuda")
-    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x), 96, N, K, 0, _ptr(o96), None, N, _stream()), "skinny 96")
-    L.check(lib.vdd_skinny_gemm(_ptr(W), _ptr(x[:20].contiguous()), 20, N, K, 0, _ptr(o20), None, N, _stream()), "skinny 20")
-    assert torch.equal(o96[:20], o20)
-
-
-def _layer_chain_case(R, H, Hl, I, Nn, seed):
-    g = torch.Generator(device="cuda").manual_seed(seed)
-    mk = lambda n, k: (torch.randn(n, k, device="cuda", generator=g) / k ** 0.5).bfloat16()
-    wo, wd, wn = mk(H, Hl), mk(H, I), mk(Nn, H)
-    gate, up = mk(I, H), mk(I, H)
-    wgu = torch.stack([gate, up], dim=1).reshape(2 * I, H).contiguous()
-    g2 = (1 + 0.1 * torch.randn(H, device="cuda", generator=g)).bfloat16()
-    g3 = (1 + 0.1 * torch.randn(H, device="cuda", generator=g)).bfloat16()
-    attn = torch.randn(R, Hl, device="cuda", generator=g).bfloat16()
-    resid = torch.randn(R, H, device="cuda", generator=g) * 2
-    return wo, wgu, gate, up, wd, wn, g2, g3, attn, resid
-
-
-@pytest.mark.parametrize("R,H,Hl,I,Nn", [(96, 4096, 4096, 11008, 12288), (16, 4096, 4096, 11008, 32000), (9, 256, 256, 512, 768),
-                                         (130, 1024, 512, 1376, 1000), (48, 5120, 1280, 3456, 3840)])
-def test_skinny_layer_chain(R, H, Hl, I, Nn):
-    """One launch = o_proj + residual, RMSNorm + gate/up + SwiGLU, down_proj + residual, RMSNorm + next projection (HF
-    LlamaDecoderLayer order), vs torch fp32 on the same bf16 weights.  The chain keeps bf16(resid * g) as the GEMM operand and
-    scales the accumulator by 1/rms afterwards; torch normalises first: same maths, different rounding point."""
-    L = _lib()
-    lib = L.load()
-    wo, wgu, gate, up, wd, wn, g2, g3, attn, resid0 = _layer_chain_case(R, H, Hl, I, Nn, R + H + I)
-    eps = 1e-5
-    rms = lambda x, gw: x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * gw.float()
-    r1 = resid0 + attn.float() @ wo.float().T
-    x1 = rms(r1, g2)
-    h = torch.nn.functional.silu(x1 @ gate.float().T) * (x1 @ up.float().T)
-    r2 = r1 + h @ wd.float().T
-    out_ref = rms(r2, g3) @ wn.float().T
-    resid = resid0.clone()
-    xg = torch.empty(R, H, device="cuda", dtype=torch.bfloat16)
-    hb = torch.empty(R, I, device="cuda", dtype=torch.bfloat16)
-    out = torch.full((R, Nn), 7.0, device="cuda")
-    run = lambda rs, o: L.check(lib.vdd_skinny_layer_chain(_ptr(attn), _ptr(rs), _ptr(wo), _ptr(g2), _ptr(wgu), _ptr(wd), _ptr(g3),
-                                                           _ptr(wn), R, H, Hl, I, Nn, eps, _ptr(xg), _ptr(hb), _ptr(o), _stream()),
-                                "layer chain")
-    run(resid, out)
-    torch.testing.assert_close(hb.float(), h, rtol=3e-2, atol=3e-2)
-    torch.testing.assert_close(resid, r2, rtol=2e-2, atol=2e-2)
-    torch.testing.assert_close(out, out_ref, rtol=3e-2, atol=3e-2)
-    # bit-identical run to run, and rows do not depend on the rows beside them
-    resid_b, out_b = resid0.clone(), torch.zeros_like(out)
-    run(resid_b, out_b)
-    assert torch.equal(out, out_b) and torch.equal(resid, resid_b)
