@@ -114,6 +114,11 @@ VDD_API int vdd_prefill_cd(vdd_engine* e, const int64_t* ids_host, int B, int T,
  * the image splice, zeros above the diagonal.  elems must equal B*heads*len*len.  out = NULL disarms.  Not under TP. */
 VDD_API int vdd_set_attention_capture(vdd_engine* e, float* out, int64_t elems);
 /* One decode step for all S*B rows: row (s,b) consumes tokens[b].  Leaves logits in vdd_logits(). */
+/* Arm the capture of the debias streams' own first-step scores for the NEXT vdd_generate / vdd_generate_cd: out receives
+ * [streams - 1][B][V] fp32 post-warper scores (same temperature / top-k / top-p, no contrast) of the unk / none / cd streams in
+ * stream order -- what the reference's post-hoc-debias drivers obtain from two extra generates per question
+ * (experiments/eval/calibrate/llava_calibrate.py:192-194 -> :62-82, `scores[0]`).  elems must equal (streams - 1) * B * V. */
+VDD_API int vdd_set_stream_scores_capture(vdd_engine* e, float* out_dev, int64_t elems);
 VDD_API int vdd_decode_step(vdd_engine* e, const int64_t* tokens, void* stream);
 VDD_API float* vdd_logits(vdd_engine* e); /* fp32 [S, B, V] */
 VDD_API int vdd_num_streams(vdd_engine* e);

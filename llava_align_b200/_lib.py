@@ -50,6 +50,7 @@ SIGNATURES = {
     "vdd_prefill_cd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vdd_prefill": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vdd_set_attention_capture": (C.c_int, [_P, _P, C.c_int64]),
+    "vdd_set_stream_scores_capture": (C.c_int, [_P, _P, C.c_int64]),
     "vdd_decode_step": (C.c_int, [_P, _P, _P]),
     "vdd_logits": (_P, [_P]),
     "vdd_num_streams": (C.c_int, [_P]),

@@ -115,6 +115,8 @@ struct vdd_engine {
   int B = 0, T = 0, S = 0, R = 0, Mtot = 0, max_new = 0, max_len = 0, max_splits = 1;
   int attn_items = 0, attn_chunk = 0;  // streaming decode attention (R > 8): (row, split) work table
   int32_t *d_item_row = nullptr, *d_item_split = nullptr;
+  float* stream_scores = nullptr;  // armed by vdd_set_stream_scores_capture: step-0 post-warper scores of the debias streams
+  int64_t stream_scores_elems = 0;
   float* attn_capture = nullptr;  // armed by vdd_set_attention_capture: the next prefill writes the last layer's step-0 map here
   int64_t attn_capture_elems = 0;
   int main_len = 0;  // length of the main-stream rows after the image splice (0: rows differ)
@@ -1072,6 +1074,12 @@ extern "C" int vdd_set_attention_capture(vdd_engine* e, float* out, int64_t elem
   e->attn_capture_elems = out ? elems : 0;
   return VDD_OK;
 }
+extern "C" int vdd_set_stream_scores_capture(vdd_engine* e, float* out, int64_t elems) {
+  if (!e) return fail(VDD_ERR_ARG, "null engine");
+  e->stream_scores = out;
+  e->stream_scores_elems = out ? elems : 0;
+  return VDD_OK;
+}
 extern "C" float* vdd_logits(vdd_engine* e) { return e ? (e->logits_cur ? e->logits_cur : (float*)e->logits.p) : nullptr; }
 extern "C" int vdd_num_streams(vdd_engine* e) { return e ? e->S : 0; }
 
@@ -1218,6 +1226,26 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
   CK(cudaMemcpyAsync(e->d_sargs, e->pinned, sizeof a, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->d_unfinished, h_unf, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   LK(e, launch_combine_sample(a, e->d_sargs, B, V, st));  // step 0 on the prefill logits
+  if (e->stream_scores) {
+    // The post-hoc-debias drivers run two MORE generates per question on the image-free prompts only to read their first-step
+    // scores (reference llava_calibrate.py:192-194 -> :62-82, scores[0]).  Those prompts are this call's debias streams: their
+    // step-0 logits already sit beside the main stream's, so the same warpers without a contrast (alpha = 0) give the scores.
+    float* out = e->stream_scores;
+    e->stream_scores = nullptr;
+    if (e->stream_scores_elems != (int64_t)(S - 1) * B * V)
+      return fail(VDD_ERR_ARG, "stream-scores buffer holds %lld floats, %d debias streams need %lld", (long long)e->stream_scores_elems,
+                  S - 1, (long long)(S - 1) * B * V);
+    for (int sidx = 1; sidx < S; ++sidx) {
+      SampleArgs b{};
+      b.l = lg + (size_t)sidx * B * V;
+      b.scores_out = out + (size_t)(sidx - 1) * B * V;
+      b.ld = V; b.B = B; b.V = V;
+      fill_sample_args(b, *p);
+      b.use_contrast = 0;
+      b.eos = -1;
+      LK(e, launch_combine_sample(b, nullptr, B, V, st));
+    }
+  }
   LK(e, launch_advance(nullptr, 0, e->d_step, st));  // step = 1
   if (use_cd) {
     // reference vcd_sample.py:148-150: model_kwargs_cd is re-copied from the MAIN stream's kwargs every step, so from

@@ -208,7 +208,7 @@ class VddEngine:
     def generate(self, input_ids: torch.Tensor, images: Optional[torch.Tensor], use_unk: bool, use_none: bool,
                  params: _lib.vdd_sample_params, max_new_tokens: int, q: Optional[torch.Tensor] = None,
                  scores_out: Optional[torch.Tensor] = None, images_cd: Optional[torch.Tensor] = None,
-                 attention_out: Optional[torch.Tensor] = None):
+                 attention_out: Optional[torch.Tensor] = None, stream_scores_out: Optional[torch.Tensor] = None):
         """attention_out: optional fp32 [B, heads, len, len] device tensor that receives the step-0 attention map of the
         last layer of the main stream (vdd_set_attention_capture)."""
         ids = input_ids.detach().to("cpu", torch.int64).contiguous()
@@ -222,6 +222,9 @@ class VddEngine:
             if not isinstance(t, torch.Tensor) or tuple(t.shape) != (B, 3, S, S):
                 got = tuple(t.shape) if isinstance(t, torch.Tensor) else type(t).__name__
                 raise ValueError(f"{what} must be a tensor of shape {(B, 3, S, S)} (one {S}px image per prompt row), got {got}")
+        if stream_scores_out is not None:
+            _lib.check(self.lib.vdd_set_stream_scores_capture(self.h, C.c_void_p(stream_scores_out.data_ptr()), stream_scores_out.numel()),
+                       "vdd_set_stream_scores_capture")
         if attention_out is not None:
             _lib.check(self.lib.vdd_set_attention_capture(self.h, C.c_void_p(attention_out.data_ptr()), attention_out.numel()),
                        "vdd_set_attention_capture")

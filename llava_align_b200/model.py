@@ -128,6 +128,9 @@ class LlavaLlamaForCausalLM:
                ("do_sample", "temperature", "top_k", "top_p", "output_scores", "output_attentions",
                 "return_dict_in_generate", "eos_token_id", "pad_token_id")}
         kwargs.pop("output_hidden_states", None)
+        # extension (not a reference kwarg): also return the debias streams' own first-step scores -- what the post-hoc-debias
+        # drivers get from two extra generates per question (llava_calibrate.py:192-194), folded into this fused batch
+        want_stream_scores = bool(kwargs.pop("return_stream_scores", False))
         if kwargs:
             raise ValueError(f"The following `model_kwargs` are not used by the model: {sorted(kwargs)}")  # HF _validate_model_kwargs
         if num_beams != 1:
@@ -188,8 +191,16 @@ class LlavaLlamaForCausalLM:
         if opt["output_attentions"] and opt["return_dict_in_generate"]:
             Tm = T + (self.vdd_config.num_patches - 1 if has_image else 0)
             attn_buf = torch.empty(B, self.vdd_config.num_attention_heads, Tm, Tm, dtype=torch.float32, device=self.device)
+        stream_names = []
+        if vdd and use_cd:
+            stream_names = (["none"] if (use_unk and use_none) else []) + ["cd"]  # engine precedence: cd replaces unk (vcd_sample.py:148)
+        elif vdd:
+            stream_names = (["unk"] if use_unk else []) + (["none"] if use_none else [])
+        ss_buf = None
+        if want_stream_scores and stream_names and opt["return_dict_in_generate"]:
+            ss_buf = torch.empty(len(stream_names), B, V, dtype=torch.float32, device=self.device)
         new_tokens, steps = self.engine.generate(input_ids, images if has_image else None, use_unk, use_none, params,
-                                                 max_new_tokens, q, scores_buf, images_cd if (vdd and use_cd) else None, attn_buf)
+                                                 max_new_tokens, q, scores_buf, images_cd if (vdd and use_cd) else None, attn_buf, ss_buf)
         seq = torch.cat([input_ids.to("cpu", torch.int64), new_tokens], dim=1).to(input_ids.device)
         if not opt["return_dict_in_generate"]:
             return seq
@@ -200,4 +211,6 @@ class LlavaLlamaForCausalLM:
         out["attentions"] = (tuple(_StepAttentions(i, L, attn_buf if i == 0 else None) for i in range(steps))
                              if attn_buf is not None else None)
         out["hidden_states"] = None
+        if ss_buf is not None:
+            out["stream_scores"] = {n: ss_buf[i] for i, n in enumerate(stream_names)}
         return out

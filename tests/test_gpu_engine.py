@@ -251,3 +251,27 @@ def test_whole_step_kernel_against_oracle(monkeypatch, B, use_unk, use_none):
     assert eng.launch_count(reset=True) > 0
     from helpers import greedy_divergence_is_near_tie
     greedy_divergence_is_near_tie(out[:, T:].cpu(), ref.sequences[:, T:], ref.stream_logits, 1.0, 0.1, 0.3)
+
+
+def test_stream_scores_fold_the_extra_generates_of_the_calibrate_driver(engine_model):
+    """llava_calibrate.py:192-194 runs two more generates per question on the image-free prompts (sentinel deleted / replaced by
+    <unk>) only to read `scores[0]`.  generate(..., return_stream_scores=True) returns those scores from the fused batch: compare
+    with the oracle's separate text-only generates on the very prompts the debias streams stand for."""
+    cfg, m, oracle = engine_model
+    from oracle.vdd_oracle import debias_ids
+    ids, img = make_inputs(cfg, 2, 13, 91)
+    kw = dict(cd_alpha=1.0, cd_beta=0.1, do_sample=True, temperature=0.7, top_k=None, top_p=None, max_new_tokens=3, eos_token_id=None)
+    out = m.generate(ids.cuda(), images=img.cuda(), use_dd=True, use_dd_unk=True, output_scores=True, return_dict_in_generate=True,
+                     return_stream_scores=True, **kw)
+    ss = out["stream_scores"]
+    assert set(ss) == {"unk", "none"} and ss["unk"].shape == (2, cfg.vocab_size)
+    for name in ("unk", "none"):
+        ref = oracle.generate(debias_ids(ids, name), None, temperature=0.7, max_new_tokens=1, output_scores=True, eos_token_id=None)
+        got = ss[name].cpu()
+        assert torch.isfinite(got).all()
+        assert (got - ref.scores[0]).abs().max().item() <= LOGIT_TOL / 0.7
+    # and what the driver does with them (utils/metrics.py:102-113): softmax -> top-10
+    probs = torch.softmax(ss["none"], dim=-1).float().cpu()
+    assert torch.topk(probs, k=10).indices.shape == (2, 10)
+    # without the flag nothing extra is returned; with no debias stream there is nothing to return
+    assert "stream_scores" not in m.generate(ids.cuda(), images=img.cuda(), use_dd=True, return_dict_in_generate=True, **kw)

@@ -1,7 +1,8 @@
-# 8-GPU session: TP=8 parity at real width, 7B headline at TP=8 (per-layer launches vs whole-step kernel), BASELINE configs[4]
-timeout 900 python -m pytest tests/test_tp_gpu.py -m gpu -q -k "real_width and 8-" > gpurun_out/r2k_tp8_tests.log 2>&1; echo "tp8 tests rc=$?"; tail -3 gpurun_out/r2k_tp8_tests.log | head -2
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
-timeout 400 $TR bench.py --gpus 8 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2k_tp8.json 2> gpurun_out/r2k_tp8.err; echo "tp8 rc=$?"; grep headline gpurun_out/r2k_tp8.err | head -1
-VDD_STEP=1 timeout 400 $TR bench.py --gpus 8 --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/r2k_tp8_step.json 2> gpurun_out/r2k_tp8_step.err; echo "tp8 step rc=$?"; grep headline gpurun_out/r2k_tp8_step.err | head -1
-timeout 900 $TR bench.py --gpus 8 --steps 3 --warmup 2 --model llava-v1.5-13b --batch 64 --flags both --no-cpu-baseline > gpurun_out/r2k_cfg4_13b_b64_tp8.json 2> gpurun_out/r2k_cfg4_13b_b64_tp8.err; echo "cfg4 rc=$?"; grep headline gpurun_out/r2k_cfg4_13b_b64_tp8.err | head -1
-tail -3 gpurun_out/r2k_cfg4_13b_b64_tp8.err
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r2l_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/r2l_tests.log | head -3
+timeout 300 python __graft_entry__.py smoke > gpurun_out/r2l_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/r2l_smoke.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2l_bench.json 2> gpurun_out/r2l_bench.err; echo "bench rc=$?"; grep -E "headline|configs" gpurun_out/r2l_bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2l_ref.json 2> gpurun_out/r2l_ref.err; echo "ref rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2l_launches.csv python bench.py --steps 1 --warmup 0 --new-tokens 6 --profile > gpurun_out/r2l_ncu1.log 2>&1; echo "ncu list rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemv_kernel -s 40 -c 2 -o gpurun_out/r2l_ncu_gemv python bench.py --steps 1 --warmup 0 --new-tokens 6 --profile > gpurun_out/r2l_ncu2.log 2>&1; echo "ncu gemv rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:combine_sample_rows_kernel -c 1 -o gpurun_out/r2l_ncu_k8rows python bench.py --steps 1 --warmup 0 --new-tokens 4 --no-cpu-baseline --no-configs --no-e2e > gpurun_out/r2l_ncu3.log 2>&1; echo "ncu k8 rc=$?"
+ls -la gpurun_out | head -30
