@@ -33,7 +33,9 @@ def test_algorithmic_bytes_match_the_survey():
     assert abs((w7 + ctx_mid * kv7 + 3 * 32000 * 4) / 1e9 - 13.77) < 0.01
 
 
-@pytest.mark.parametrize("name", ["r1_bench_n1_latest.json", "r1_bench_config3_b32.json", "r1_bench_dp2.json", "r1_bench_tp2_fused.json"])
+@pytest.mark.parametrize("name", ["r1_bench_n1_latest.json", "r1_bench_config3_b32.json", "r1_bench_dp2.json", "r1_bench_tp2_fused.json",
+                                  "r2_bench_n1.json", "r2_bench_tp2.json", "r2_bench_tp4.json", "r2_bench_tp8.json",
+                                  "r2_bench_config3_13b_b8_tp4.json"])
 def test_committed_bench_lines_carry_the_contract_keys(name):
     d = json.load(open(os.path.join(ROOT, "profiles", name)))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
@@ -57,3 +59,24 @@ def test_reference_arm_line():
     d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_reference_arm.json")))
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_round2_line_carries_configs_block_and_tp_default():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_n1.json")))
+    c = d["configs"]["configs[2]"]
+    for k in ("workload", "value", "unit", "e2e", "decode_step", "roofline", "gpu_launches"):
+        assert k in c, k
+    assert "batch 32" in c["workload"] and c["value"] > 0 and c["e2e"]["h2d_bytes_per_step"] > 0
+    assert all(x["how"].startswith("200 launches in one CUDA graph") for x in d["logit_combine"] if x["B"] <= 64)
+    assert d["cpu_baseline"]["kind"] == "port" and "FULL depth" in d["cpu_baseline"]["sample"]
+    for n in (2, 4, 8):
+        t = json.load(open(os.path.join(ROOT, "profiles", f"r2_bench_tp{n}.json")))
+        assert t["n_gpus"] == n and t["scaling"] == "strong" and t["config"]["parallelism"].startswith(f"tp{n}")
+
+
+def test_round2_reference_arm_fits_its_wall_clock():
+    """the reference arm claimed 92.6 s per step inside a 45 s run.  ms_per_step is now the measured wall time of a sample."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_reference_arm.json")))
+    assert d["impl"] == "reference" and d["value_kind"].startswith("projected")
+    assert d["ms_per_step"] * d["steps"] < 120e3 and d["projected_ms_per_full_generate"] > d["ms_per_step"]
+    assert "FULL depth" in d["cpu_baseline"]["sample"]
