@@ -114,6 +114,19 @@ VDD_API int vdd_prefill_cd(vdd_engine* e, const int64_t* ids_host, int B, int T,
  * the image splice, zeros above the diagonal.  elems must equal B*heads*len*len.  out = NULL disarms.  Not under TP. */
 VDD_API int vdd_set_attention_capture(vdd_engine* e, float* out, int64_t elems);
 /* One decode step for all S*B rows: row (s,b) consumes tokens[b].  Leaves logits in vdd_logits(). */
+/* Sampling variates from the caller's torch CUDA generator state instead of an explicit q_exp: the NEXT vdd_generate* with
+ * q_exp == NULL draws, inside K8, exactly the Exp(1) numbers torch.multinomial(probs, 1) (reference vcd_sample.py:202) would draw
+ * on this device -- call `step` of `empty([B, V]).exponential_(1)` with the generator at (seed, offset + step * stride): Philox4x32-10
+ * as cuRAND runs it for ATen, ATen's element -> (thread, call, component) mapping, -log(u).  After the call the caller advances
+ * its generator by vdd_sampler_rng_advance() (= steps * stride) to stay in step with the reference.  offset % 4 == 0.            */
+VDD_API int vdd_set_sampler_rng(vdd_engine* e, uint64_t seed, uint64_t offset);
+VDD_API uint64_t vdd_sampler_rng_advance(vdd_engine* e);
+/* Test aid: out_dev[i] = element i of `torch.empty(numel, device='cuda').exponential_(1)` under (seed, offset). */
+VDD_API int vdd_debug_philox_exponential(uint64_t seed, uint64_t offset, int64_t numel, float* out_dev, void* stream);
+/* Ragged batches: mask_host [B, T] bytes, 1 = token, 0 = padding (left or right), applies to the NEXT prefill / generate only (NULL
+ * disarms).  Masked positions do not exist for any stream: a padded row computes exactly what the same prompt computes alone.  The
+ * reference has no working equivalent (its decode step rebuilds the mask as all ones, llava_arch.py:91-94). */
+VDD_API int vdd_set_prompt_mask(vdd_engine* e, const uint8_t* mask_host, int B, int T);
 /* Arm the capture of the debias streams' own first-step scores for the NEXT vdd_generate / vdd_generate_cd: out receives
  * [streams - 1][B][V] fp32 post-warper scores (same temperature / top-k / top-p, no contrast) of the unk / none / cd streams in
  * stream order -- what the reference's post-hoc-debias drivers obtain from two extra generates per question

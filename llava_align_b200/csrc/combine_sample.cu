@@ -18,6 +18,57 @@
 
 namespace vdd {
 
+// ------------------------------------------------------------------------------------------------ torch's exponential_ stream
+// Philox4x32-10 exactly as cuRAND runs it for ATen (curand_init(seed, subsequence = thread index, offset) + curand_uniform4), the
+// element -> (thread, call, component) mapping of ATen's distribution_elementwise_grid_stride_kernel (block 256, unroll 4,
+// grid = min(#SM * maxThreadsPerSM / 256, ceil(numel / 256))) and transformation::exponential (-log(u), log clamped at 1).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float torch_exponential_from_bits(unsigned x) {
+  const float u = __fmaf_rn(__uint2float_rn(x), 2.3283064e-10f, 1.1641532e-10f);  // curand_uniform: (0, 1]
+  const float lg = u >= 1.0f - 5.9604645e-08f ? -5.9604645e-08f : logf(u);        // at::transformation::exponential (CUDA branch)
+  return -lg;
+}
+__device__ __forceinline__ float philox_q(const SampleArgs& a, int step, long long li) {
+  const unsigned T = a.philox_threads;
+  const unsigned idx = (unsigned)(li % T);
+  const unsigned j = (unsigned)(li / T);
+  const unsigned long long ctr = (a.philox_offset + (unsigned long long)step * a.philox_stride) / 4ull + (j >> 2);
+  const uint4 r = philox4x32_10(make_uint4((unsigned)ctr, (unsigned)(ctr >> 32), idx, 0u),
+                                make_uint2((unsigned)a.philox_seed, (unsigned)(a.philox_seed >> 32)));
+  const unsigned comp = j & 3u;
+  return torch_exponential_from_bits(comp == 0 ? r.x : (comp == 1 ? r.y : (comp == 2 ? r.z : r.w)));
+}
+void sample_philox_geometry(SampleArgs& a, long long numel, int num_sms, int max_threads_per_sm) {
+  unsigned long long grid = (unsigned long long)((numel + 255) / 256);
+  const unsigned long long cap = (unsigned long long)num_sms * (unsigned long long)(max_threads_per_sm / 256);
+  if (grid > cap) grid = cap;
+  a.philox_threads = (unsigned)(256ull * grid);
+  a.philox_stride = ((unsigned long long)(numel - 1) / (256ull * grid * 4ull) + 1ull) * 4ull;
+}
+__global__ void philox_exponential_kernel(SampleArgs a, long long numel, float* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x)
+    out[i] = philox_q(a, 0, i);
+}
+cudaError_t launch_philox_exponential(unsigned long long seed, unsigned long long offset, long long numel, int num_sms,
+                                      int max_threads_per_sm, float* out, cudaStream_t stream) {
+  SampleArgs a{};
+  a.philox_seed = seed;
+  a.philox_offset = offset;
+  sample_philox_geometry(a, numel, num_sms, max_threads_per_sm);
+  philox_exponential_kernel<<<296, 256, 0, stream>>>(a, numel, out);
+  return cudaGetLastError();
+}
+
 constexpr int CS_THREADS = 1024;
 constexpr int CS_ITEMS = 32;  // V <= 32768
 
@@ -259,13 +310,15 @@ __global__ void __launch_bounds__(CS_THREADS, 1) combine_sample_kernel(const Sam
     const int e = j * CS_THREADS + tid;
     if (scores_out && e < V) scores_out[e] = v[j];
   }
-  if (q) {
+  if (q || a.use_philox) {
     // torch.multinomial(softmax(s), 1) == argmax_e softmax(s)_e / q_e == argmax_e (s_e - log q_e): the normaliser and the
     // row maximum cancel in the ORDER, so neither the sum of exponentials nor a second row reduction is needed.
 #pragma unroll
     for (int j = 0; j < CS_ITEMS; ++j) {
       const int e = j * CS_THREADS + tid;
-      v[j] = e < V ? v[j] - logf(__ldg(q + e)) : -INFINITY;
+      // masked entries lose the race whatever their variate: skip their Philox rounds
+      if (e < V) v[j] = q ? v[j] - logf(__ldg(q + e)) : (v[j] > -INFINITY ? v[j] - logf(philox_q(a, step, (long long)b * V + e)) : v[j]);
+      else v[j] = -INFINITY;
     }
   }
   // argmax, lowest index on ties: pack (orderable key bits, ~index) into 64 bits
@@ -387,11 +440,12 @@ combine_sample_cluster_kernel(const SampleArgs byval, const SampleArgs* dptr) {
     const int e = e0 + j * CC_THREADS;
     if (scores_out && e < V) scores_out[e] = v[j];
   }
-  if (q) {  // argmax_e softmax(s)_e / q_e == argmax_e (s_e - log q_e): no normaliser, no second row reduction
+  if (q || a.use_philox) {  // argmax_e softmax(s)_e / q_e == argmax_e (s_e - log q_e): no normaliser, no second row reduction
 #pragma unroll
     for (int j = 0; j < CC_ITEMS; ++j) {
       const int e = e0 + j * CC_THREADS;
-      v[j] = e < V ? v[j] - logf(__ldg(q + e)) : -INFINITY;
+      if (e < V) v[j] = q ? v[j] - logf(__ldg(q + e)) : (v[j] > -INFINITY ? v[j] - logf(philox_q(a, step, (long long)b * V + e)) : v[j]);
+      else v[j] = -INFINITY;
     }
   }
   unsigned long long best = 0ull;
@@ -529,7 +583,12 @@ __global__ void __launch_bounds__(CR_THREADS, 1) combine_sample_rows_kernel(cons
             }
             if (temp != 1.0f) v[e] = __fdiv_rn(v[e], temp);
             if (topk1) m2 = fmaxf(m2, v[e]);
-            else best = max(best, race_key(q ? v[e] - logf(qv[e]) : v[e], i * 4 + e));
+            else {
+              float rv = v[e];
+              if (q) rv = v[e] - logf(qv[e]);
+              else if (a.use_philox && v[e] > -INFINITY) rv = v[e] - logf(philox_q(a, step, (long long)b * V + i * 4 + e));
+              best = max(best, race_key(rv, i * 4 + e));
+            }
           }
           s4[i] = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -551,7 +610,12 @@ __global__ void __launch_bounds__(CR_THREADS, 1) combine_sample_rows_kernel(cons
           float4 qv4 = q ? __ldg(q4 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
           const float qv[4] = {qv4.x, qv4.y, qv4.z, qv4.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) best = max(best, race_key(q ? v[e] - logf(qv[e]) : v[e], i * 4 + e));
+          for (int e = 0; e < 4; ++e) {
+            float rv = v[e];
+            if (q) rv = v[e] - logf(qv[e]);
+            else if (a.use_philox && v[e] > -INFINITY) rv = v[e] - logf(philox_q(a, step, (long long)b * V + i * 4 + e));
+            best = max(best, race_key(rv, i * 4 + e));
+          }
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) best = max(best, race_key(-INFINITY, i * 4 + e));

@@ -115,6 +115,11 @@ struct vdd_engine {
   int B = 0, T = 0, S = 0, R = 0, Mtot = 0, max_new = 0, max_len = 0, max_splits = 1;
   int attn_items = 0, attn_chunk = 0;  // streaming decode attention (R > 8): (row, split) work table
   int32_t *d_item_row = nullptr, *d_item_split = nullptr;
+  bool rng_armed = false;            // armed by vdd_set_sampler_rng: the next generate draws its variates in the kernel
+  unsigned long long rng_seed = 0, rng_offset = 0, rng_advance = 0;
+  int max_threads_per_sm = 2048;
+  std::vector<uint8_t> prompt_mask;  // armed by vdd_set_prompt_mask: [B*T] 1 = real token, 0 = padding (next prefill only)
+  int prompt_mask_B = 0, prompt_mask_T = 0;
   float* stream_scores = nullptr;  // armed by vdd_set_stream_scores_capture: step-0 post-warper scores of the debias streams
   int64_t stream_scores_elems = 0;
   float* attn_capture = nullptr;  // armed by vdd_set_attention_capture: the next prefill writes the last layer's step-0 map here
@@ -215,6 +220,7 @@ extern "C" int vdd_create(const vdd_config* cfg, vdd_engine** out) {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&e->max_threads_per_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
   e->use_pdl = getenv("VDD_NO_PDL") == nullptr;
   e->use_graph = getenv("VDD_NO_GRAPH") == nullptr;
   e->use_fused = getenv("VDD_NO_FUSED") == nullptr;
@@ -613,6 +619,13 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   if (use_unk) kinds.push_back(1);
   if (use_none) kinds.push_back(2);
   if (use_cd) kinds.push_back(3);  // last: its rows are dropped after step 0 (vdd_generate_cd)
+  // ragged batches: positions masked out by the caller (padding, left or right) simply do not exist for any stream, so a padded
+  // row behaves exactly like the same prompt submitted alone (the reference cannot do this: its decode step rebuilds the mask
+  // as all ones, llava_arch.py:91-94)
+  std::vector<uint8_t> pmask;
+  pmask.swap(e->prompt_mask);  // one-shot
+  if (!pmask.empty() && (e->prompt_mask_B != B || e->prompt_mask_T != T))
+    return fail(VDD_ERR_ARG, "prompt mask is %dx%d, the prompt %dx%d", e->prompt_mask_B, e->prompt_mask_T, B, T);
   std::vector<int32_t> tok, img_row, row_seq, row_pos, seqlen(R), q_row0(R), kv_cap(R), last_rows(R);
   std::vector<int64_t> kv_off(R), head_stride(R);
   int64_t kv_total = 0;
@@ -623,6 +636,7 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
       q_row0[q] = (int32_t)tok.size();
       int nsent = 0, pos = 0;
       for (int t = 0; t < T; ++t) {
+        if (!pmask.empty() && !pmask[(size_t)b * T + t]) continue;  // padding
         const int64_t id = ids[(size_t)b * T + t];
         if (id == VDD_IMAGE_TOKEN_INDEX) {
           ++nsent;
@@ -1074,6 +1088,34 @@ extern "C" int vdd_set_attention_capture(vdd_engine* e, float* out, int64_t elem
   e->attn_capture_elems = out ? elems : 0;
   return VDD_OK;
 }
+extern "C" int vdd_set_sampler_rng(vdd_engine* e, uint64_t seed, uint64_t offset) {
+  if (!e) return fail(VDD_ERR_ARG, "null engine");
+  if (offset % 4) return fail(VDD_ERR_ARG, "a torch CUDA generator offset is a multiple of 4");
+  e->rng_armed = true;
+  e->rng_seed = seed;
+  e->rng_offset = offset;
+  return VDD_OK;
+}
+extern "C" uint64_t vdd_sampler_rng_advance(vdd_engine* e) { return e ? e->rng_advance : 0; }
+extern "C" int vdd_debug_philox_exponential(uint64_t seed, uint64_t offset, int64_t numel, float* out_dev, void* stream_v) {
+  if (!out_dev || numel <= 0) return fail(VDD_ERR_ARG, "bad argument");
+  int dev = 0, sms = 148, mt = 2048;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&mt, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+  cudaError_t ce = launch_philox_exponential(seed, offset, numel, sms, mt, out_dev, (cudaStream_t)stream_v);
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "philox_exponential: %s", cudaGetErrorString(ce));
+  return VDD_OK;
+}
+extern "C" int vdd_set_prompt_mask(vdd_engine* e, const uint8_t* mask_host, int B, int T) {
+  if (!e) return fail(VDD_ERR_ARG, "null engine");
+  if (!mask_host) { e->prompt_mask.clear(); e->prompt_mask_B = e->prompt_mask_T = 0; return VDD_OK; }
+  if (B <= 0 || T <= 0) return fail(VDD_ERR_ARG, "bad mask shape");
+  e->prompt_mask.assign(mask_host, mask_host + (size_t)B * T);
+  e->prompt_mask_B = B;
+  e->prompt_mask_T = T;
+  return VDD_OK;
+}
 extern "C" int vdd_set_stream_scores_capture(vdd_engine* e, float* out, int64_t elems) {
   if (!e) return fail(VDD_ERR_ARG, "null engine");
   e->stream_scores = out;
@@ -1215,6 +1257,18 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
   a.unfinished = e->d_unfinished; a.step_ptr = e->d_step; a.ld = V; a.B = B; a.V = V;
   fill_sample_args(a, *p);
   a.use_contrast = (p->use_contrast && S > 1) ? 1 : 0;
+  // Variates: explicit q_exp (tests, callers that drew them), or generated inside K8 from the caller's torch generator state so that
+  // the tokens are the ones the reference's torch.multinomial would draw on this device under the same seed -- one exponential_
+  // call on [B, V] per step; the generator is advanced by the caller afterwards (vdd_sampler_rng_advance).
+  e->rng_advance = 0;
+  const bool rng = e->rng_armed;
+  e->rng_armed = false;
+  if (rng) {
+    sample_philox_geometry(a, (long long)B * V, e->num_sms, e->max_threads_per_sm);
+    a.philox_seed = e->rng_seed;
+    a.philox_offset = e->rng_offset;
+    a.use_philox = q_exp == nullptr ? 1 : 0;
+  }
   if (e->pinned_bytes < sizeof(SampleArgs) + (size_t)B * 4 + 64) {
     if (e->pinned) cudaFreeHost(e->pinned);
     e->pinned_bytes = sizeof(SampleArgs) + (size_t)B * 4 + 4096;
@@ -1360,6 +1414,7 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
     }
   }
   if (steps_out) *steps_out = steps;
+  if (rng) e->rng_advance = (unsigned long long)steps * a.philox_stride;  // `steps` exponential_ calls, as the reference's loop makes
   cudaEventElapsedTime(&e->t_vision, e->ev[0], e->ev[1]);
   cudaEventElapsedTime(&e->t_prefill, e->ev[1], e->ev[2]);
   cudaEventElapsedTime(&e->t_decode, e->ev[2], e->ev[3]);

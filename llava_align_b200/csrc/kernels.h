@@ -17,7 +17,17 @@ struct SampleArgs {
   int64_t ld, seq_ld, eos, pad;
   int B, V, top_k, use_contrast;
   float one_plus_alpha, alpha, log_beta, temperature, top_p;
+  // q == null and use_philox: the Exp(1) variates are generated in the kernel, bit for bit the ones the reference draws --
+  // torch.multinomial(probs, 1) on CUDA = probs.div(empty_like(probs).exponential_(1)).argmax: call number `step` of
+  // exponential_ on a [B, V] fp32 tensor with the generator at (philox_seed, philox_offset + step * philox_stride)
+  int use_philox;
+  unsigned philox_threads;             // threads of torch's distribution kernel for B*V elements (256 * grid.x)
+  unsigned long long philox_seed, philox_offset, philox_stride;
 };
+// fill philox_threads / philox_stride the way ATen's calc_execution_policy does for numel elements on this device
+void sample_philox_geometry(SampleArgs& a, long long numel, int num_sms, int max_threads_per_sm);
+cudaError_t launch_philox_exponential(unsigned long long seed, unsigned long long offset, long long numel, int num_sms,
+                                      int max_threads_per_sm, float* out, cudaStream_t stream);  // debug / tests: q as torch draws it
 cudaError_t launch_combine_sample(const SampleArgs& args, const SampleArgs* dptr, int B, int V, cudaStream_t stream);
 
 // ---------------------------------------------------------------- decode GEMV (R <= 8 rows of x against W[N,K])

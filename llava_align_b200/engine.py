@@ -186,9 +186,27 @@ class VddEngine:
         P, H = self.cfg.num_patches, self.cfg.hidden_size
         return torch.as_tensor(_DevPtr(self.lib.vdd_image_features(self.h), (B, P, H), "<f4"), device=self.device)
 
-    def prefill(self, input_ids: torch.Tensor, with_images: bool, use_unk: bool, use_none: bool, max_new_tokens: int):
+    def set_sampler_rng(self, seed: int, offset: int):
+        """The next generate() without an explicit q draws its Exp(1) variates inside K8 from this torch-generator state."""
+        _lib.check(self.lib.vdd_set_sampler_rng(self.h, C.c_uint64(seed & (2 ** 64 - 1)), C.c_uint64(offset)), "vdd_set_sampler_rng")
+
+    def sampler_rng_advance(self) -> int:
+        return int(self.lib.vdd_sampler_rng_advance(self.h))
+
+    def set_prompt_mask(self, attention_mask: Optional[torch.Tensor]):
+        """Ragged batch: [B, T] mask (nonzero = token) for the next prefill / generate; None disarms."""
+        if attention_mask is None:
+            _lib.check(self.lib.vdd_set_prompt_mask(self.h, None, 0, 0), "vdd_set_prompt_mask")
+            return
+        m = (attention_mask.detach().to("cpu") != 0).to(torch.uint8).contiguous()
+        _lib.check(self.lib.vdd_set_prompt_mask(self.h, C.c_void_p(m.data_ptr()), m.shape[0], m.shape[1]), "vdd_set_prompt_mask")
+
+    def prefill(self, input_ids: torch.Tensor, with_images: bool, use_unk: bool, use_none: bool, max_new_tokens: int,
+                attention_mask: Optional[torch.Tensor] = None):
         ids = input_ids.detach().to("cpu", torch.int64).contiguous()
         B, T = ids.shape
+        if attention_mask is not None:
+            self.set_prompt_mask(attention_mask)
         _lib.check(self.lib.vdd_prefill(self.h, C.c_void_p(ids.data_ptr()), B, T, int(with_images), int(use_unk), int(use_none),
                                         int(max_new_tokens), _stream_ptr(self.device)), "vdd_prefill")
         self._B = B
@@ -208,7 +226,8 @@ class VddEngine:
     def generate(self, input_ids: torch.Tensor, images: Optional[torch.Tensor], use_unk: bool, use_none: bool,
                  params: _lib.vdd_sample_params, max_new_tokens: int, q: Optional[torch.Tensor] = None,
                  scores_out: Optional[torch.Tensor] = None, images_cd: Optional[torch.Tensor] = None,
-                 attention_out: Optional[torch.Tensor] = None, stream_scores_out: Optional[torch.Tensor] = None):
+                 attention_out: Optional[torch.Tensor] = None, stream_scores_out: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None):
         """attention_out: optional fp32 [B, heads, len, len] device tensor that receives the step-0 attention map of the
         last layer of the main stream (vdd_set_attention_capture)."""
         ids = input_ids.detach().to("cpu", torch.int64).contiguous()
@@ -222,6 +241,8 @@ class VddEngine:
             if not isinstance(t, torch.Tensor) or tuple(t.shape) != (B, 3, S, S):
                 got = tuple(t.shape) if isinstance(t, torch.Tensor) else type(t).__name__
                 raise ValueError(f"{what} must be a tensor of shape {(B, 3, S, S)} (one {S}px image per prompt row), got {got}")
+        if attention_mask is not None:
+            self.set_prompt_mask(attention_mask)
         if stream_scores_out is not None:
             _lib.check(self.lib.vdd_set_stream_scores_capture(self.h, C.c_void_p(stream_scores_out.data_ptr()), stream_scores_out.numel()),
                        "vdd_set_stream_scores_capture")

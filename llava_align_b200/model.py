@@ -140,10 +140,16 @@ class LlavaLlamaForCausalLM:
             raise NotImplementedError("custom stopping_criteria are not supported: EOS and max_new_tokens stop generation")
         if input_ids.dim() == 1:
             input_ids = input_ids.unsqueeze(0)
+        ragged = None
         if attention_mask is not None and not bool(torch.as_tensor(attention_mask).bool().all()):
-            # the reference rebuilds the decode-step mask as all ones (llava_arch.py:91-94): padded
-            # batches are not a supported input there either; refuse instead of attending to pad tokens
-            raise NotImplementedError("padded prompts (attention_mask with zeros) are not supported: pass equal-length rows")
+            # Ragged batch (designed, not copied: the reference rebuilds the decode-step mask as all ones, llava_arch.py:91-94,
+            # SURVEY Appendix A Q8, so its padded batches attend to pad tokens).  Masked positions -- left or right padding --
+            # do not exist for any stream: every row computes what the same prompt computes alone.
+            ragged = torch.as_tensor(attention_mask)
+            if tuple(ragged.shape) != tuple(input_ids.shape):
+                raise ValueError(f"attention_mask {tuple(ragged.shape)} does not match input_ids {tuple(input_ids.shape)}")
+            if bool(((input_ids == IMAGE_TOKEN_INDEX) & (ragged.to(input_ids.device) == 0)).any()):
+                raise ValueError("the image sentinel of a row is masked out")
         B, T = input_ids.shape
         if max_new_tokens is None:
             max_new_tokens = gc.max_new_tokens
@@ -181,14 +187,31 @@ class LlavaLlamaForCausalLM:
             params = _engine.make_sample_params(use_contrast=False, eos_token_id=eos, pad_token_id=pad)
         V = self.vdd_config.vocab_size
         q = None
-        if do_sample and params.top_k != 1:
-            # torch.multinomial(probs, 1) == argmax(probs / Exp(1)); the variates come from torch's CUDA generator
-            q = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device).exponential_(1)
-            q = self.engine.tp_broadcast(q)  # tensor parallel: every rank must race against rank 0's variates
+        gen = None
+        if do_sample:
+            # torch.multinomial(probs, 1) == argmax(probs / q), q = empty_like(probs).exponential_(1) from torch's CUDA generator.
+            # K8 regenerates exactly those numbers from the generator's (seed, offset) -- nothing of size [steps, B, V] is
+            # allocated -- and the generator is advanced afterwards as if the reference's loop had drawn them.
+            # VDD_TORCH_Q=1: draw them with torch up front instead (one [steps, B, V] call: a different stream of numbers).
+            import os
+            if os.environ.get("VDD_TORCH_Q"):
+                if params.top_k != 1:
+                    q = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device).exponential_(1)
+                    q = self.engine.tp_broadcast(q)  # tensor parallel: every rank must race against rank 0's variates
+            else:
+                gen = torch.cuda.default_generators[self.device.index if self.device.index is not None else torch.cuda.current_device()]
+                s64 = gen.initial_seed() & (2 ** 64 - 1)
+                state = torch.tensor([s64 - 2 ** 64 if s64 >= 2 ** 63 else s64, gen.get_offset()], dtype=torch.int64, device=self.device)
+                state = self.engine.tp_broadcast(state)  # tensor parallel: rank 0's generator decides for all ranks
+                seed, offset = (int(x) for x in state.tolist())
+                seed &= 2 ** 64 - 1
+                self.engine.set_sampler_rng(seed, offset)
         want_scores = bool(opt["output_scores"] and opt["return_dict_in_generate"])
         scores_buf = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device) if want_scores else None
         attn_buf = None
         if opt["output_attentions"] and opt["return_dict_in_generate"]:
+            if ragged is not None:
+                raise NotImplementedError("attention maps need rows of equal length")
             Tm = T + (self.vdd_config.num_patches - 1 if has_image else 0)
             attn_buf = torch.empty(B, self.vdd_config.num_attention_heads, Tm, Tm, dtype=torch.float32, device=self.device)
         stream_names = []
@@ -200,7 +223,10 @@ class LlavaLlamaForCausalLM:
         if want_stream_scores and stream_names and opt["return_dict_in_generate"]:
             ss_buf = torch.empty(len(stream_names), B, V, dtype=torch.float32, device=self.device)
         new_tokens, steps = self.engine.generate(input_ids, images if has_image else None, use_unk, use_none, params,
-                                                 max_new_tokens, q, scores_buf, images_cd if (vdd and use_cd) else None, attn_buf, ss_buf)
+                                                 max_new_tokens, q, scores_buf, images_cd if (vdd and use_cd) else None, attn_buf, ss_buf,
+                                                 ragged)
+        if gen is not None:
+            gen.set_offset(offset + self.engine.sampler_rng_advance())
         seq = torch.cat([input_ids.to("cpu", torch.int64), new_tokens], dim=1).to(input_ids.device)
         if not opt["return_dict_in_generate"]:
             return seq

@@ -275,3 +275,64 @@ def test_stream_scores_fold_the_extra_generates_of_the_calibrate_driver(engine_m
     assert torch.topk(probs, k=10).indices.shape == (2, 10)
     # without the flag nothing extra is returned; with no debias stream there is nothing to return
     assert "stream_scores" not in m.generate(ids.cuda(), images=img.cuda(), use_dd=True, return_dict_in_generate=True, **kw)
+
+
+def test_ragged_batch_rows_equal_the_same_prompts_alone(engine_model):
+    """Ragged batches: left- and right-padded rows under an attention_mask compute exactly what the unpadded
+    prompts compute alone -- every stream's logits at every step against the oracle run row by row on the unpadded prompts,
+    and generate() end to end.  (The reference itself cannot batch ragged prompts: llava_arch.py:91-94.)"""
+    cfg, m, oracle = engine_model
+    T, n = 14, 4
+    ids, img = make_inputs(cfg, 3, T, 61)          # sentinel at column 1 + T // 8 = 2
+    mask = torch.ones(3, T, dtype=torch.long)
+    ids[1, :3] = cfg.pad_token_id; mask[1, :3] = 0    # left padding ...
+    ids[1, 5] = -200; ids[1, 2] = cfg.pad_token_id    # ... with the sentinel moved inside the real part
+    ids[2, 9:] = cfg.pad_token_id; mask[2, 9:] = 0    # right padding
+    rows = [ids[b][mask[b] != 0].unsqueeze(0) for b in range(3)]
+    refs = [oracle.generate(rows[b], img[b:b + 1], use_dd=True, use_dd_unk=True, cd_alpha=1.0, cd_beta=0.1, top_k=1, max_new_tokens=n,
+                            keep_stream_logits=True, eos_token_id=None) for b in range(3)]
+    eng = m.engine
+    eng.encode_images(img)
+    lg = eng.prefill(ids, True, True, True, n, attention_mask=mask)
+    for step in range(n):
+        got = lg.cpu()
+        for b in range(3):
+            for si, nm in enumerate("mud"):
+                err = (got[si, b] - refs[b].stream_logits[step][nm][0]).abs().max().item()
+                assert err <= LOGIT_TOL, (step, b, nm, err)
+        if step + 1 < n:
+            lg = eng.decode_step(torch.stack([refs[b].sequences[0, rows[b].shape[1] + step] for b in range(3)]))
+    out = m.generate(ids.cuda(), images=img.cuda(), attention_mask=mask.cuda(), use_dd=True, use_dd_unk=True, cd_alpha=1.0, cd_beta=0.1,
+                     do_sample=True, top_k=1, max_new_tokens=n, eos_token_id=None)
+    assert out.shape == (3, T + n) and torch.equal(out[:, :T].cpu(), ids)
+    from helpers import greedy_divergence_is_near_tie
+    for b in range(3):
+        ref_new = refs[b].sequences[:, rows[b].shape[1]:]
+        greedy_divergence_is_near_tie(out[b:b + 1, T:].cpu(), ref_new, refs[b].stream_logits, 1.0, 0.1, 0.3)
+    with pytest.raises(ValueError):   # a masked-out sentinel is a caller error
+        bad = mask.clone(); bad[0, 2] = 0
+        m.generate(ids.cuda(), images=img.cuda(), attention_mask=bad.cuda(), use_dd=True, do_sample=True, max_new_tokens=2, eos_token_id=None)
+
+
+@pytest.mark.parametrize("B,sampler", [(1, dict(top_k=None, top_p=None, temperature=1.0)), (2, dict(top_k=None, top_p=0.9, temperature=0.8)),
+                                       (2, dict(top_k=1))])
+def test_generate_draws_the_variates_torch_multinomial_would(engine_model, B, sampler):
+    """model.generate() takes its randomness from torch's CUDA generator like the reference (torch.multinomial per step): the
+    tokens equal a run that is handed the per-step `empty(B, V).exponential_(1)` draws explicitly, and the generator ends where
+    that loop leaves it."""
+    cfg, m, oracle = engine_model
+    from llava_align_b200 import engine as E
+    ids, img = make_inputs(cfg, B, 12, 700 + B)
+    n, V = 7, cfg.vocab_size
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    torch.manual_seed(99)
+    qs = torch.stack([torch.empty(B, V, device="cuda").exponential_(1) for _ in range(n)])
+    end_offset = gen.get_offset()
+    params = E.make_sample_params(cd_alpha=1.0, cd_beta=0.1, temperature=sampler.get("temperature"), top_k=sampler.get("top_k"),
+                                  top_p=sampler.get("top_p"), use_contrast=True, eos_token_id=None, pad_token_id=cfg.pad_token_id)
+    want, steps = m.engine.generate(ids, img, True, True, params, n, qs, None)
+    torch.manual_seed(99)
+    out = m.generate(ids.cuda(), images=img.cuda(), use_dd=True, use_dd_unk=True, cd_alpha=1.0, cd_beta=0.1, do_sample=True,
+                     max_new_tokens=n, eos_token_id=None, **sampler)
+    assert torch.equal(out[:, 12:].cpu(), want.cpu())
+    assert gen.get_offset() == end_offset

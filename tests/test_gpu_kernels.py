@@ -110,6 +110,27 @@ def test_combine_sample_rows_kernel_eos_and_ties():
         assert torch.equal(unf.cpu(), exp_unf)
 
 
+@pytest.mark.parametrize("B,V", [(1, 32000), (2, 512), (3, 1000), (32, 32000), (64, 32000), (200, 32000)])
+def test_in_kernel_variates_are_torchs_exponential_stream(B, V):
+    """K8 can draw its Exp(1) variates itself from a torch generator state; they must be, bit for bit, what
+    `torch.empty(B, V, device='cuda').exponential_(1)` -- the draw inside torch.multinomial(probs, 1), reference vcd_sample.py:202 --
+    produces under that state: Philox4x32-10, ATen's thread / call / component mapping (grid capped at #SM * 8 blocks: B * V beyond
+    303104 elements wraps onto the components, beyond 1.2 M onto further calls), -log(u), and the per-call offset stride."""
+    L = _lib()
+    lib = L.load()
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    torch.manual_seed(1234 + B)
+    torch.rand(7, device="cuda")                      # move the offset off zero
+    for call in range(2):
+        seed, off = gen.initial_seed(), gen.get_offset()
+        ref = torch.empty(B, V, device="cuda").exponential_(1)
+        stride = gen.get_offset() - off
+        got = torch.empty(B, V, device="cuda")
+        L.check(lib.vdd_debug_philox_exponential(C.c_uint64(seed), C.c_uint64(off), B * V, _ptr(got), _stream()), "philox")
+        assert torch.equal(got, ref), (call, (got != ref).sum().item(), got.flatten()[:4], ref.flatten()[:4])
+        assert stride % 4 == 0 and stride > 0
+
+
 def test_combine_sample_ties_split_by_top_p():
     """Equal scores straddling the top-p boundary: HF's stable ascending sort removes the LOWER indices first."""
     from llava_align_b200.engine import logit_combine_sample
