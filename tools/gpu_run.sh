@@ -1,2 +1,1 @@
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2m_tests.log 2>&1; echo "tests rc=$?"; tail -12 gpurun_out/r2m_tests.log | grep -vE "Warning|warn|^$|fork|import" | head -12
-timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2m_bench.json 2> gpurun_out/r2m_bench.err; echo "bench rc=$?"; grep -E "headline|configs" gpurun_out/r2m_bench.err; tail -3 gpurun_out/r2m_bench.err
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2o_tests.log 2>&1; echo "tests rc=$?"; grep -E "passed|failed|FAILED" gpurun_out/r2o_tests.log | tail -8
