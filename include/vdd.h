@@ -123,6 +123,14 @@ VDD_API int vdd_set_sampler_rng(vdd_engine* e, uint64_t seed, uint64_t offset);
 VDD_API uint64_t vdd_sampler_rng_advance(vdd_engine* e);
 /* Test aid: out_dev[i] = element i of `torch.empty(numel, device='cuda').exponential_(1)` under (seed, offset). */
 VDD_API int vdd_debug_philox_exponential(uint64_t seed, uint64_t offset, int64_t numel, float* out_dev, void* stream);
+/* Test aid: one launch of the varlen prefill attention (llava_llama.py:91-100 at step 0, clip_encoder.py:48) on caller-provided device
+ * buffers.  q is bf16 [q_rows, q_ld]; k / v are bf16 [kv_rows, k_tok_stride]; key t of (sequence s, head h) starts at element
+ * k_off[s] + h*k_head_stride[s] + t*k_tok_stride; out is bf16 addressed like q with out_ld.  use_tc: 1 = tcgen05 + TMA kernel, 0 = the
+ * mma.sync kernel. */
+VDD_API int vdd_debug_prefill_attn(const void* q, int64_t q_ld, int64_t q_rows, const void* k, const void* v, int64_t kv_rows,
+                                   int64_t k_tok_stride, const int64_t* k_off, const int64_t* k_head_stride, const int32_t* q_row0,
+                                   const int32_t* seqlen, void* out, int64_t out_ld, int nseq, int heads, int max_seqlen, int causal,
+                                   int head_dim, float scale, int use_tc, void* stream);
 /* Ragged batches: mask_host [B, T] bytes, 1 = token, 0 = padding (left or right), applies to the NEXT prefill / generate only (NULL
  * disarms).  Masked positions do not exist for any stream: a padded row computes exactly what the same prompt computes alone.  The
  * reference has no working equivalent (its decode step rebuilds the mask as all ones, llava_arch.py:91-94). */

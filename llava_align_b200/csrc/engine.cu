@@ -560,6 +560,7 @@ static int encode_images_slot(vdd_engine* e, const void* pixels, int B, int slot
     pa.k_off = d_off; pa.k_head_stride = d_hs; pa.k_tok_stride = 3 * VH;
     pa.q_row0 = d_q0; pa.seqlen = d_len; pa.out = att; pa.out_ld = VH;
     pa.nseq = B; pa.heads = c.v_heads; pa.max_seqlen = NT; pa.causal = 0; pa.head_dim = 64; pa.scale = 0.125f;
+    pa.q_rows = Mv; pa.kv_rows = Mv;
     LK(e, launch_prefill_attn(pa, st));
     RC(do_gemm(e, att, w.wo, Mv, VH, VH, GEMM_OUT_ADD_F32, w.bo, nullptr, res, nullptr, VH, st));
     LK(e, launch_layernorm(res, w.ln2w, w.ln2b, c.v_ln_eps, xn, nullptr, Mv, VH, nullptr, st));
@@ -698,7 +699,13 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   RC(ensure(e, e->qb, (size_t)Mtot * Hl * 2));
   RC(ensure(e, e->attn, (size_t)Mtot * Hl * 2));
   RC(ensure(e, e->hbuf, (size_t)Mtot * Il * 2));
-  RC(ensure(e, e->kv, (size_t)2 * L * kv_total * 2));
+  {
+    // The tcgen05 prefill attention multiplies P = 0 with the V rows between a sequence's end and the end of its last 64-key
+    // tile: a fresh allocation may hold NaN bit patterns there, data of earlier generates is finite.  Zero once per allocation.
+    const void* before = e->kv.p;
+    RC(ensure(e, e->kv, (size_t)2 * L * kv_total * 2));
+    if (e->kv.p != before) CK(cudaMemsetAsync(e->kv.p, 0, e->kv.bytes, st));
+  }
   RC(ensure(e, e->logits, (size_t)R * c.vocab_size * 4));
   if (R > 8 && R <= 128) RC(ensure(e, e->split_ws, (size_t)8 * R * H * 4));
   if (c.tp_size > 1) {
@@ -784,6 +791,7 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
     pa.k_tok_stride = 128; pa.q_row0 = e->d_q_row0; pa.seqlen = e->d_seqlen; pa.out = e->attn.p; pa.out_ld = Hl;
     pa.nseq = R; pa.heads = e->heads_l; pa.max_seqlen = max_len; pa.causal = 1; pa.head_dim = 128;
     pa.scale = 0.08838834764831845f;  // 1/sqrt(128)
+    pa.q_rows = Mtot; pa.kv_rows = kv_total / 128;
     LK(e, launch_prefill_attn(pa, st));
     if (c.tp_size > 1) {
       RC(do_gemm(e, e->attn.p, w.wo, Mtot, H, Hl, GEMM_OUT_F32, nullptr, nullptr, (float*)e->tp_tmp.p, nullptr, H, st));
@@ -1080,6 +1088,19 @@ extern "C" int vdd_decode_step(vdd_engine* e, const int64_t* tokens, void* strea
   cudaStream_t st = (cudaStream_t)stream_v;
   RC(decode_step_enqueue(e, tokens, st));
   LK(e, launch_advance(e->d_pos, e->R, nullptr, st, e->d_epoch));  // pos += 1 (and the TP epoch)
+  return VDD_OK;
+}
+extern "C" int vdd_debug_prefill_attn(const void* q, int64_t q_ld, int64_t q_rows, const void* k, const void* v, int64_t kv_rows,
+                                      int64_t k_tok_stride, const int64_t* k_off, const int64_t* k_head_stride, const int32_t* q_row0,
+                                      const int32_t* seqlen, void* out, int64_t out_ld, int nseq, int heads, int max_seqlen, int causal,
+                                      int head_dim, float scale, int use_tc, void* stream) {
+  if (!q || !k || !v || !k_off || !k_head_stride || !q_row0 || !seqlen || !out) return fail(VDD_ERR_ARG, "null argument");
+  PrefillAttnArgs pa{};
+  pa.q = q; pa.q_ld = q_ld; pa.k = k; pa.v = v; pa.k_off = k_off; pa.k_head_stride = k_head_stride; pa.k_tok_stride = k_tok_stride;
+  pa.q_row0 = q_row0; pa.seqlen = seqlen; pa.out = out; pa.out_ld = out_ld; pa.nseq = nseq; pa.heads = heads; pa.max_seqlen = max_seqlen;
+  pa.causal = causal; pa.head_dim = head_dim; pa.scale = scale; pa.q_rows = q_rows; pa.kv_rows = kv_rows;
+  const cudaError_t ce = use_tc ? launch_prefill_attn_tc(pa, (cudaStream_t)stream) : launch_prefill_attn_mma(pa, (cudaStream_t)stream);
+  if (ce != cudaSuccess) return fail(VDD_ERR_CUDA, "prefill attention (%s): %s", use_tc ? "tcgen05" : "mma.sync", cudaGetErrorString(ce));
   return VDD_OK;
 }
 extern "C" int vdd_set_attention_capture(vdd_engine* e, float* out, int64_t elems) {

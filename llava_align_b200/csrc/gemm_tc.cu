@@ -395,6 +395,16 @@ static bool make_tmap(CUtensorMap* m, const void* ptr, int rows, int K, int box_
   return r == CUDA_SUCCESS;
 }
 
+bool make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows) {
+  if (!gemm_init() || rows <= 0 || cols < GM_BK || box_rows <= 0 || box_rows > 256 || (pitch_elems % 8) || ((uintptr_t)ptr & 15)) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+  cuuint32_t box[2] = {GM_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (!gemm_init()) return cudaErrorNotSupported;
   if (a.M <= 0) return cudaSuccess;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+struct CUtensorMap_st;  // <cuda.h>'s CUtensorMap, for files that do not include it
+
 namespace vdd {
 
 // ---------------------------------------------------------------- K8 combine + sample
@@ -200,8 +202,17 @@ struct PrefillAttnArgs {
   int64_t out_ld;
   int nseq, heads, max_seqlen, causal, head_dim;
   float scale;
+  // tcgen05 kernel only (0 => the mma.sync kernel): extents of the buffers behind q and k / v for the TMA tensor maps --
+  // q is [q_rows, q_ld], k and v are [kv_rows, k_tok_stride] (k_off + h*k_head_stride must put a head's 64-column boxes inside a row)
+  int64_t q_rows = 0, kv_rows = 0;
 };
+// tcgen05 + TMA kernel (prefill_attn_tc.cu) when the layout allows it, else / with VDD_PREFILL_ATTN_MMA=1 the mma.sync kernel
 cudaError_t launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t stream);
+cudaError_t launch_prefill_attn_mma(const PrefillAttnArgs& a, cudaStream_t stream);
+cudaError_t launch_prefill_attn_tc(const PrefillAttnArgs& a, cudaStream_t stream);
+bool prefill_attn_tc_supported(const PrefillAttnArgs& a);
+// 2-D bf16 row-major tensor map [rows, cols] with row pitch `pitch_elems`, box {64, box_rows}, 128-byte swizzle (gemm_tc.cu)
+bool make_tmap_bf16_2d(::CUtensorMap_st* m, const void* ptr, int64_t rows, int64_t cols, int64_t pitch_elems, int box_rows);
 
 // step-0 attention map of one layer for the first B sequences (all of length len): out [B, heads, len, len] fp32
 struct AttnProbsArgs {

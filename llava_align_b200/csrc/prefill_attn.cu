@@ -8,6 +8,8 @@
 // padded shared memory, S = QK^T and O += PV on mma.sync m16n8k16 (bf16 in, fp32 accumulate), online softmax in the
 // exp2 domain.  Attention is <2% of the prefill FLOPs, so this kernel stays on the legacy MMA path in
 // round 1; the GEMMs that dominate are tcgen05 (gemm_tc.cu).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -178,6 +180,12 @@ static cudaError_t launch_pa(const PrefillAttnArgs& a, cudaStream_t stream) {
 }
 
 cudaError_t launch_prefill_attn(const PrefillAttnArgs& a, cudaStream_t stream) {
+  static const bool legacy = getenv("VDD_PREFILL_ATTN_MMA") != nullptr;
+  if (!legacy && prefill_attn_tc_supported(a)) return launch_prefill_attn_tc(a, stream);
+  return launch_prefill_attn_mma(a, stream);
+}
+
+cudaError_t launch_prefill_attn_mma(const PrefillAttnArgs& a, cudaStream_t stream) {
   if (a.nseq <= 0 || a.max_seqlen <= 0) return cudaSuccess;
   if (a.head_dim == 128) return a.causal ? launch_pa<128, true>(a, stream) : launch_pa<128, false>(a, stream);
   if (a.head_dim == 64) return a.causal ? launch_pa<64, true>(a, stream) : launch_pa<64, false>(a, stream);

@@ -230,3 +230,93 @@ def test_gemm_epilogues(M, N, K):
     exp = torch.zeros(M, N, device="cuda")
     exp[rm[1:].long()] = ref[1:]
     torch.testing.assert_close(out, exp, **tol)
+
+
+# ------------------------------------------------------------------------------------------------ prefill attention
+def _attn_reference(q, k, v, causal, scale):
+    """fp32 eager attention of one (sequence, head): q [n, D], k / v [n, D] (HF LlamaAttention / CLIPAttention eager path)."""
+    s = (q.float() @ k.float().T) * scale
+    if causal:
+        n = q.shape[0]
+        s = s.masked_fill(torch.ones(n, n, dtype=torch.bool, device=q.device).triu(1), float("-inf"))
+    return torch.softmax(s, dim=-1) @ v.float()
+
+
+def _run_prefill_attn(q, q_ld, q_rows, k, v, kv_rows, tok, k_off, hs, q0, lens, out, out_ld, heads, causal, D, scale, use_tc):
+    L = _lib()
+    lib = L.load()
+    dev = q.device
+    d_off = torch.tensor(k_off, dtype=torch.int64, device=dev)
+    d_hs = torch.tensor(hs, dtype=torch.int64, device=dev)
+    d_q0 = torch.tensor(q0, dtype=torch.int32, device=dev)
+    d_len = torch.tensor(lens, dtype=torch.int32, device=dev)
+    L.check(lib.vdd_debug_prefill_attn(_ptr(q), q_ld, q_rows, _ptr(k), _ptr(v), kv_rows, tok, _ptr(d_off), _ptr(d_hs), _ptr(d_q0), _ptr(d_len),
+                                       _ptr(out), out_ld, len(lens), heads, max(lens), int(causal), D, C.c_float(scale), int(use_tc),
+                                       _stream()), "prefill_attn")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("lens", [[607, 32, 31], [128], [129, 64, 1], [863, 257]])
+def test_prefill_attn_tc_llm_layout(lens):
+    """tcgen05 + TMA prefill attention on the LLM layout (head_dim 128, causal, keys in a head-major cache with slack rows that
+    hold NaN -- the kernel must never let them through) against fp32 eager attention and against the mma.sync kernel."""
+    torch.manual_seed(sum(lens))
+    dev, heads, D = "cuda", 4, 128
+    Hl = heads * D
+    Mtot = sum(lens)
+    q = (torch.randn(Mtot, Hl, device=dev) * 1.5).bfloat16()
+    caps = [n + 40 for n in lens]
+    kv_total = sum(c * Hl for c in caps)
+    # K slack rows: NaN (scores are masked by select).  V slack rows: finite garbage (the engine zeroes fresh caches; see engine.cu)
+    kc = torch.full((kv_total,), float("nan"), device=dev, dtype=torch.bfloat16)
+    vc = torch.full((kv_total,), 7.0, device=dev, dtype=torch.bfloat16)
+    k_off, hs, q0, ref = [], [], [], torch.zeros(Mtot, Hl, device=dev)
+    off = r0 = 0
+    for n, cap in zip(lens, caps):
+        k_off.append(off); hs.append(cap * D); q0.append(r0)
+        for h in range(heads):
+            ks = (torch.randn(n, D, device=dev)).bfloat16()
+            vs = (torch.randn(n, D, device=dev)).bfloat16()
+            base = off + h * cap * D
+            kc[base:base + n * D] = ks.flatten()
+            vc[base:base + n * D] = vs.flatten()
+            ref[r0:r0 + n, h * D:(h + 1) * D] = _attn_reference(q[r0:r0 + n, h * D:(h + 1) * D], ks, vs, True, D ** -0.5)
+        off += cap * Hl
+        r0 += n
+    outs = []
+    for use_tc in (1, 0):
+        out = torch.full((Mtot, Hl), float("nan"), device=dev, dtype=torch.bfloat16)
+        _run_prefill_attn(q, Hl, Mtot, kc, vc, kv_total // 128, 128, k_off, hs, q0, lens, out, Hl, heads, True, D, D ** -0.5, use_tc)
+        outs.append(out.float())
+    tc, mma = outs
+    assert torch.isfinite(tc).all()
+    # P is rounded to bf16 before P.V (as the reference rounds to fp16) and the output is bf16: 2e-2 absolute on O(1) values
+    assert (tc - ref).abs().max().item() < 2e-2, (tc - ref).abs().max().item()
+    assert (tc - mma).abs().max().item() < 2e-2, (tc - mma).abs().max().item()
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_prefill_attn_tc_vit_layout(B):
+    """The same kernel on the vision tower's layout: head_dim 64, non-causal, q | k | v interleaved in one [rows, 3*VH] buffer."""
+    torch.manual_seed(B)
+    dev, heads, D, NT = "cuda", 4, 64, 577
+    VH = heads * D
+    rows = B * NT
+    qkv = (torch.randn(rows, 3 * VH, device=dev)).bfloat16()
+    ref = torch.zeros(rows, VH, device=dev)
+    for b in range(B):
+        r = slice(b * NT, (b + 1) * NT)
+        for h in range(heads):
+            c = slice(h * D, (h + 1) * D)
+            ref[r, c] = _attn_reference(qkv[r, :VH][:, c], qkv[r, VH:2 * VH][:, c], qkv[r, 2 * VH:][:, c], False, 0.125)
+    k_off = [b * NT * 3 * VH for b in range(B)]
+    outs = []
+    for use_tc in (1, 0):
+        out = torch.full((rows, VH), float("nan"), device=dev, dtype=torch.bfloat16)
+        _run_prefill_attn(qkv, 3 * VH, rows, qkv[:, VH:], qkv[:, 2 * VH:], rows, 3 * VH, k_off, [D] * B, [b * NT for b in range(B)],
+                          [NT] * B, out, VH, heads, False, D, 0.125, use_tc)
+        outs.append(out.float())
+    tc, mma = outs
+    assert torch.isfinite(tc).all()
+    assert (tc - ref).abs().max().item() < 2e-2, (tc - ref).abs().max().item()
+    assert (tc - mma).abs().max().item() < 2e-2, (tc - mma).abs().max().item()

@@ -1,5 +1,4 @@
-# L2 prefetch of the next chain's weights from the few-row attention kernel: sweep
-for mb in 0 32 64 100 160; do
-  VDD_ATTN_L2_MB=$mb timeout 300 python bench.py --steps 5 --warmup 3 --no-configs --no-cpu-baseline > gpurun_out/r2q_l2_$mb.json 2> gpurun_out/r2q_l2_$mb.err
-  echo "mb=$mb rc=$? $(python -c "import json;d=json.loads(open('gpurun_out/r2q_l2_$mb.json').read());print(round(d['value'],1), d['decode_step']['ms_per_token_step'], d['roofline']['frac'])")"
-done
+# launch list of one configs[2]-shape prefill (+ ViT) under ncu: where do the 370 ms go
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2s_prefill_launches.csv \
+  python bench.py --profile --batch 32 --prompt-len 64 --new-tokens 2 --steps 1 --warmup 0 --no-configs > gpurun_out/r2s.log 2>&1; echo "ncu rc=$?"
+wc -l gpurun_out/r2s_prefill_launches.csv
