@@ -113,6 +113,11 @@ VDD_API int vdd_prefill_cd(vdd_engine* e, const int64_t* ids_host, int B, int T,
  * (llava_calibrate.py:180-182, vcd_sample.py:241-246) -- into out: fp32 [B, heads, len, len], len = prompt length after
  * the image splice, zeros above the diagonal.  elems must equal B*heads*len*len.  out = NULL disarms.  Not under TP. */
 VDD_API int vdd_set_attention_capture(vdd_engine* e, float* out, int64_t elems);
+/* The whole `attentions` tuple of generate(output_attentions=True) (vcd_sample.py:241-246: the MAIN stream's per-layer maps, one entry
+ * per step), for the NEXT vdd_generate* only.  step0: fp32 [L, B, heads, len, len] (attentions[0][l]); later: fp32
+ * [max_new_tokens - 1, L, B, heads, len + max_new_tokens - 1], row (s-1, l, b, h) = attentions[s][l][b, h, 0, :len + s] followed by
+ * zeros.  Either may be NULL.  The decode steps of such a call run as plain launches (no CUDA graph).  Not under TP. */
+VDD_API int vdd_set_attention_capture_all(vdd_engine* e, float* step0, int64_t step0_elems, float* later, int64_t later_elems);
 /* One decode step for all S*B rows: row (s,b) consumes tokens[b].  Leaves logits in vdd_logits(). */
 /* Sampling variates from the caller's torch CUDA generator state instead of an explicit q_exp: the NEXT vdd_generate* with
  * q_exp == NULL draws, inside K8, exactly the Exp(1) numbers torch.multinomial(probs, 1) (reference vcd_sample.py:202) would draw

@@ -50,6 +50,7 @@ SIGNATURES = {
     "vdd_prefill_cd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vdd_prefill": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vdd_set_attention_capture": (C.c_int, [_P, _P, C.c_int64]),
+    "vdd_set_attention_capture_all": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64]),
     "vdd_set_sampler_rng": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
     "vdd_sampler_rng_advance": (C.c_uint64, [_P]),
     "vdd_debug_philox_exponential": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, _P, _P]),

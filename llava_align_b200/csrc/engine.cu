@@ -124,6 +124,11 @@ struct vdd_engine {
   int64_t stream_scores_elems = 0;
   float* attn_capture = nullptr;  // armed by vdd_set_attention_capture: the next prefill writes the last layer's step-0 map here
   int64_t attn_capture_elems = 0;
+  // armed by vdd_set_attention_capture_all for the next generate: every layer's step-0 map and every later step's rows
+  float* attn_all0 = nullptr;   // [L, B, heads, len, len]
+  float* attn_alln = nullptr;   // [max_new - 1, L, B, heads, len + max_new - 1]
+  int64_t attn_all0_elems = 0, attn_alln_elems = 0;
+  int attn_all_w = 0;           // row width of attn_alln, set by the generate that consumes it
   int main_len = 0;  // length of the main-stream rows after the image splice (0: rows differ)
   std::vector<int32_t> h_item_row;
   int64_t kv_layer_stride = 0;
@@ -793,6 +798,18 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
     pa.scale = 0.08838834764831845f;  // 1/sqrt(128)
     pa.q_rows = Mtot; pa.kv_rows = kv_total / 128;
     LK(e, launch_prefill_attn(pa, st));
+    if (e->attn_all0) {  // attentions[0][l]: this layer's roped queries are in qb, its keys in the cache
+      if (c.tp_size > 1) return fail(VDD_ERR_UNSUPPORTED, "attention maps are not gathered across tensor-parallel ranks");
+      if (!e->main_len) return fail(VDD_ERR_UNSUPPORTED, "attention maps need main-stream rows of equal length");
+      const int64_t per_layer = (int64_t)B * e->heads_l * e->main_len * e->main_len;
+      if (per_layer * L != e->attn_all0_elems)
+        return fail(VDD_ERR_ARG, "step-0 attention buffer holds %lld floats, %d layers need %lld", (long long)e->attn_all0_elems, L,
+                    (long long)(per_layer * L));
+      AttnProbsArgs ap{};
+      ap.q = e->qb.p; ap.q_ld = Hl; ap.k = kc; ap.k_off = e->d_kv_off; ap.kv_cap = e->d_kv_cap; ap.q_row0 = e->d_q_row0;
+      ap.out = e->attn_all0 + (size_t)l * per_layer; ap.B = B; ap.heads = e->heads_l; ap.len = e->main_len; ap.scale = 0.08838834764831845f;
+      LK(e, launch_attn_probs(ap, st));
+    }
     if (c.tp_size > 1) {
       RC(do_gemm(e, e->attn.p, w.wo, Mtot, H, Hl, GEMM_OUT_F32, nullptr, nullptr, (float*)e->tp_tmp.p, nullptr, H, st));
       RC(tp_allreduce_add(e, (float*)e->tp_tmp.p, resid, (int64_t)Mtot * H, st));
@@ -940,7 +957,7 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     return g;
   };
   if (fused) CK(cudaMemsetAsync(e->d_bar, 0, (size_t)(L + 2) * 4 * 4, st));
-  if (fused && e->step_ready && e->step_R == R) {
+  if (fused && e->step_ready && e->step_R == R && !e->attn_alln) {
     // ONE persistent launch for the whole step (decode_step.cu): weights streamed by a producer warp across all phases
     if (!projections_only) LK(e, launch_decode_embed(e->embed, tokens, e->resid_d, e->B, e->S, H, st));
     StepArgs sa{};
@@ -1000,6 +1017,13 @@ static int decode_step_enqueue(vdd_engine* e, const int64_t* tokens, cudaStream_
     da.R = R; da.heads = e->heads_l; da.max_splits = e->max_splits; da.scale = 0.08838834764831845f;
     if (e->attn_items) { da.item_row = e->d_item_row; da.item_split = e->d_item_split; da.n_items = e->attn_items; da.chunk = e->attn_chunk; }
     if (!projections_only) LK(e, launch_decode_attn(da, st));
+    if (e->attn_alln && !projections_only) {  // attentions[step][l] of the main rows; qkv_d still holds this layer's query
+      AttnProbsDecodeArgs ap{};
+      ap.qkv = e->qkv_d; ap.k = da.kcache; ap.k_off = e->d_kv_off; ap.kv_cap = e->d_kv_cap; ap.pos = e->d_pos; ap.rope_cos = e->rope_cos;
+      ap.rope_sin = e->rope_sin; ap.step = e->d_step; ap.out = e->attn_alln; ap.B = e->B; ap.heads = e->heads_l; ap.layers = L; ap.layer = l;
+      ap.W = e->attn_all_w; ap.scale = 0.08838834764831845f;
+      LK(e, launch_attn_probs_decode(ap, st));
+    }
     if (fused) {
       GemvChain ch{};
       const int res_epi = tpf ? GEMV_OUT_TP_PARTIAL : GEMV_OUT_ADD_RESID;
@@ -1107,6 +1131,14 @@ extern "C" int vdd_set_attention_capture(vdd_engine* e, float* out, int64_t elem
   if (!e) return fail(VDD_ERR_ARG, "null engine");
   e->attn_capture = out;
   e->attn_capture_elems = out ? elems : 0;
+  return VDD_OK;
+}
+extern "C" int vdd_set_attention_capture_all(vdd_engine* e, float* step0, int64_t step0_elems, float* later, int64_t later_elems) {
+  if (!e) return fail(VDD_ERR_ARG, "null engine");
+  e->attn_all0 = step0;
+  e->attn_all0_elems = step0 ? step0_elems : 0;
+  e->attn_alln = later;
+  e->attn_alln_elems = later ? later_elems : 0;
   return VDD_OK;
 }
 extern "C" int vdd_set_sampler_rng(vdd_engine* e, uint64_t seed, uint64_t offset) {
@@ -1264,6 +1296,21 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
   }
   CK(cudaEventRecord(e->ev[1], st));
   RC(prefill_impl(e, ids, B, T, pixels_host != nullptr, use_unk, use_none, use_cd ? 1 : 0, max_new, st));
+  e->attn_all0 = nullptr;  // consumed by the prefill
+  if (e->attn_alln) {      // rows of the later steps: [max_new - 1, L, B, heads, len + max_new - 1]
+    if (max_new < 2) {
+      e->attn_alln = nullptr;
+    } else {
+      if (c.tp_size > 1 || !e->main_len) { e->attn_alln = nullptr; return fail(VDD_ERR_UNSUPPORTED, "attention maps: one rank, main-stream rows of equal length"); }
+      e->attn_all_w = e->main_len + max_new - 1;
+      const int64_t need = (int64_t)(max_new - 1) * c.num_layers * B * e->heads_l * e->attn_all_w;
+      if (need != e->attn_alln_elems) {
+        e->attn_alln = nullptr;
+        return fail(VDD_ERR_ARG, "decode attention buffer holds %lld floats, %d steps need %lld", (long long)e->attn_alln_elems, max_new - 1,
+                    (long long)need);
+      }
+    }
+  }
   const int V = c.vocab_size;
   int S = e->S;
   // device-resident sampler arguments: the graph reads them through a pointer, so one graph serves every call
@@ -1373,7 +1420,8 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
     mix((uint64_t)e->max_new); mix((uint64_t)(uintptr_t)e->d_sargs); mix((uint64_t)(uintptr_t)e->d_bar);
     mix((uint64_t)(uintptr_t)e->d_item_row); mix((uint64_t)(uintptr_t)e->d_seq_out);
     int per_step_launches = 0;
-    const bool graph = e->use_graph && st != nullptr;  // the legacy default stream cannot be captured
+    // the legacy default stream cannot be captured; a full attention capture adds per-layer launches: those steps run eagerly
+    const bool graph = e->use_graph && st != nullptr && !e->attn_alln;
     if (graph && (!e->graph_exec || e->graph_key != key)) {
       if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
       cudaGraph_t g = nullptr;
@@ -1434,6 +1482,7 @@ extern "C" int vdd_generate_cd(vdd_engine* e, const int64_t* ids, int B, int T, 
       if (!any) { steps = i + 1; break; }
     }
   }
+  e->attn_alln = nullptr;  // the capture applies to one generate
   if (steps_out) *steps_out = steps;
   if (rng) e->rng_advance = (unsigned long long)steps * a.philox_stride;  // `steps` exponential_ calls, as the reference's loop makes
   cudaEventElapsedTime(&e->t_vision, e->ev[0], e->ev[1]);

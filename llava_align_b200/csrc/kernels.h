@@ -228,6 +228,23 @@ struct AttnProbsArgs {
 };
 cudaError_t launch_attn_probs(const AttnProbsArgs& a, cudaStream_t stream);
 
+// attention row of one decode step and one layer for the first B rows (the main stream): out[step-1][layer][b][h][0..W), the first
+// pos[b]+1 entries are softmax(q k^T / sqrt(d)) over the row's cache (the new key included), the rest zero
+struct AttnProbsDecodeArgs {
+  const float* qkv;   // fp32 [R, 3*heads*128] of the step (q | k | v), pre-RoPE
+  const void* k;      // bf16 K cache of the layer, as in AttnProbsArgs
+  const int64_t* k_off;
+  const int32_t* kv_cap;
+  const int32_t* pos;       // [R] position of the new token
+  const float* rope_cos;    // [max_pos, 64]
+  const float* rope_sin;
+  const int32_t* step;      // device step counter (>= 1 during decode)
+  float* out;
+  int B, heads, layers, layer, W;
+  float scale;
+};
+cudaError_t launch_attn_probs_decode(const AttnProbsDecodeArgs& a, cudaStream_t stream);
+
 // ---------------------------------------------------------------- element-wise / glue
 cudaError_t launch_rmsnorm_bf16(const float* x, const void* w_bf16, float eps, void* out_bf16, int rows, int H,
                                 const int32_t* row_idx, cudaStream_t stream, bool pdl = false);

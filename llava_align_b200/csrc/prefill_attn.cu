@@ -237,6 +237,62 @@ __global__ void __launch_bounds__(AP_THREADS) attn_probs_kernel(const AttnProbsA
   for (int j = tid; j < a.len; j += AP_THREADS) o[j] = j <= i ? ap_sc[j] * inv : 0.f;
 }
 
+// The same for a decode step (`attentions[step][layer]`, step >= 1: [B, heads, 1, len + step]): the query of the new token is roped
+// here from the step's fp32 qkv row; the layer's cache already holds the new key (decode_attn_kernel ran).  One CTA per (head, row).
+__global__ void __launch_bounds__(AP_THREADS) attn_probs_decode_kernel(const AttnProbsDecodeArgs a) {
+  extern __shared__ float ap_sc[];  // [W]
+  __shared__ float q_s[128];
+  __shared__ float red[33];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int pos = a.pos[b], ctx = pos + 1;
+  {
+    const float* qh = a.qkv + (size_t)b * 3 * a.heads * 128 + h * 128;
+    const int i = tid & 63;
+    const float c = a.rope_cos[(size_t)pos * 64 + i], s = a.rope_sin[(size_t)pos * 64 + i];
+    const float x1 = qh[i], x2 = qh[i + 64];
+    q_s[tid] = tid < 64 ? (x1 * c - x2 * s) : (x2 * c + x1 * s);
+  }
+  __syncthreads();
+  const __nv_bfloat16* K = reinterpret_cast<const __nv_bfloat16*>(a.k) + a.k_off[b] + (size_t)h * a.kv_cap[b] * 128;
+  float mx = -INFINITY;
+  for (int j = tid; j < ctx; j += AP_THREADS) {
+    const uint4* kr = reinterpret_cast<const uint4*>(K + (size_t)j * 128);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const uint4 w = kr[c];
+      const float* qq = q_s + c * 8;
+      s += bf16lo(w.x) * qq[0] + bf16hi(w.x) * qq[1] + bf16lo(w.y) * qq[2] + bf16hi(w.y) * qq[3] + bf16lo(w.z) * qq[4] +
+           bf16hi(w.z) * qq[5] + bf16lo(w.w) * qq[6] + bf16hi(w.w) * qq[7];
+    }
+    s *= a.scale;
+    ap_sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_reduce<true>(mx, red);
+  float sum = 0.f;
+  for (int j = tid; j < ctx; j += AP_THREADS) {
+    const float e = expf(ap_sc[j] - mx);
+    ap_sc[j] = e;
+    sum += e;
+  }
+  sum = block_reduce<false>(sum, red);
+  const float inv = 1.f / sum;
+  float* o = a.out + ((((size_t)(*a.step - 1) * a.layers + a.layer) * a.B + b) * a.heads + h) * a.W;
+  for (int j = tid; j < a.W; j += AP_THREADS) o[j] = j < ctx ? ap_sc[j] * inv : 0.f;
+}
+
+cudaError_t launch_attn_probs_decode(const AttnProbsDecodeArgs& a, cudaStream_t stream) {
+  if (a.B <= 0 || a.W <= 0) return cudaSuccess;
+  const size_t smem = (size_t)a.W * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(attn_probs_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  attn_probs_decode_kernel<<<dim3(a.heads, a.B), AP_THREADS, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_attn_probs(const AttnProbsArgs& a, cudaStream_t stream) {
   if (a.B <= 0 || a.len <= 0) return cudaSuccess;
   const size_t smem = (size_t)a.len * 4;

@@ -227,9 +227,11 @@ class VddEngine:
                  params: _lib.vdd_sample_params, max_new_tokens: int, q: Optional[torch.Tensor] = None,
                  scores_out: Optional[torch.Tensor] = None, images_cd: Optional[torch.Tensor] = None,
                  attention_out: Optional[torch.Tensor] = None, stream_scores_out: Optional[torch.Tensor] = None,
-                 attention_mask: Optional[torch.Tensor] = None):
+                 attention_mask: Optional[torch.Tensor] = None, attention_all_out=None):
         """attention_out: optional fp32 [B, heads, len, len] device tensor that receives the step-0 attention map of the
-        last layer of the main stream (vdd_set_attention_capture)."""
+        last layer of the main stream (vdd_set_attention_capture).  attention_all_out: optional pair of fp32 device tensors
+        ([L, B, heads, len, len], [max_new-1, L, B, heads, len+max_new-1] or None) for every layer and step
+        (vdd_set_attention_capture_all)."""
         ids = input_ids.detach().to("cpu", torch.int64).contiguous()
         B, T = ids.shape
         # the library copies B*3*S*S elements from the raw pointer: refuse anything else (the reference also accepts lists and
@@ -249,6 +251,11 @@ class VddEngine:
         if attention_out is not None:
             _lib.check(self.lib.vdd_set_attention_capture(self.h, C.c_void_p(attention_out.data_ptr()), attention_out.numel()),
                        "vdd_set_attention_capture")
+        if attention_all_out is not None:
+            a0, an = attention_all_out
+            _lib.check(self.lib.vdd_set_attention_capture_all(self.h, C.c_void_p(a0.data_ptr()), a0.numel(),
+                                                              C.c_void_p(an.data_ptr()) if an is not None else None,
+                                                              an.numel() if an is not None else 0), "vdd_set_attention_capture_all")
         px = None
         if images is not None:
             # host (ideally pinned) pixels are copied by the library inside the call; device pixels are used in place

@@ -41,10 +41,10 @@ class GenerateOutput(dict):
 
 
 class _StepAttentions(tuple):
-    """`attentions[step]`: HF returns one tensor per layer.  The fused kernels never materialise attention matrices; the
-    map the reference's drivers actually read -- step 0, LAST layer (`attentions[0][-1]`, llava_calibrate.py:180,
-    MME/run_llava.py:218) -- is computed after the prefill from the last layer's queries and K cache.  Any other entry
-    raises instead of returning something made up."""
+    """`attentions[step]` when only the map the reference's drivers read was materialised -- step 0, LAST layer
+    (`attentions[0][-1]`, llava_calibrate.py:180, MME/run_llava.py:218), computed after the prefill from the last layer's
+    queries and K cache.  Any other entry raises instead of returning something made up.  The full tuple (every step, every
+    layer) is returned instead when it fits `VDD_ATTENTIONS_MAX_GB` (default 4) or `VDD_ATTENTIONS=all` is set."""
 
     def __new__(cls, step, num_layers, last_layer_map):
         self = super().__new__(cls, ())
@@ -57,11 +57,22 @@ class _StepAttentions(tuple):
     def __getitem__(self, i):
         if isinstance(i, int) and (i == -1 or i == self._L - 1) and self._map is not None:
             return self._map
-        raise NotImplementedError(f"attentions[{self._step}][{i}] is not materialised: only attentions[0][-1] (step 0, last layer, "
-                                  f"main stream) is available from the fused path")
+        raise NotImplementedError(f"attentions[{self._step}][{i}] was not materialised: this generate kept only attentions[0][-1] "
+                                  f"(step 0, last layer, main stream) because the full tuple exceeds VDD_ATTENTIONS_MAX_GB; "
+                                  f"set VDD_ATTENTIONS=all to capture every step and layer")
 
     def __iter__(self):
-        raise NotImplementedError("only attentions[0][-1] is materialised by the fused path")
+        raise NotImplementedError("only attentions[0][-1] was materialised (set VDD_ATTENTIONS=all for the full tuple)")
+
+
+def _attention_capture_mode(B, heads, L, len0, max_new):
+    """'all' when the whole `attentions` tuple (vcd_sample.py:241-246) fits the budget, else 'last' (what the drivers read)."""
+    import os
+    mode = os.environ.get("VDD_ATTENTIONS", "auto")
+    if mode in ("all", "last"):
+        return mode
+    total = 4 * B * heads * L * (len0 * len0 + max(max_new - 1, 0) * (len0 + max_new - 1))
+    return "all" if total <= float(os.environ.get("VDD_ATTENTIONS_MAX_GB", "4")) * 2 ** 30 else "last"
 
 
 class _VisionTowerHandle:
@@ -208,12 +219,18 @@ class LlavaLlamaForCausalLM:
                 self.engine.set_sampler_rng(seed, offset)
         want_scores = bool(opt["output_scores"] and opt["return_dict_in_generate"])
         scores_buf = torch.empty(max_new_tokens, B, V, dtype=torch.float32, device=self.device) if want_scores else None
-        attn_buf = None
+        attn_buf = attn_all = None
         if opt["output_attentions"] and opt["return_dict_in_generate"]:
             if ragged is not None:
                 raise NotImplementedError("attention maps need rows of equal length")
             Tm = T + (self.vdd_config.num_patches - 1 if has_image else 0)
-            attn_buf = torch.empty(B, self.vdd_config.num_attention_heads, Tm, Tm, dtype=torch.float32, device=self.device)
+            nh, nl = self.vdd_config.num_attention_heads, self.vdd_config.num_hidden_layers
+            if _attention_capture_mode(B, nh, nl, Tm, max_new_tokens) == "all":
+                attn_all = (torch.empty(nl, B, nh, Tm, Tm, dtype=torch.float32, device=self.device),
+                            torch.zeros(max_new_tokens - 1, nl, B, nh, Tm + max_new_tokens - 1, dtype=torch.float32, device=self.device)
+                            if max_new_tokens > 1 else None)
+            else:
+                attn_buf = torch.empty(B, nh, Tm, Tm, dtype=torch.float32, device=self.device)
         stream_names = []
         if vdd and use_cd:
             stream_names = (["none"] if (use_unk and use_none) else []) + ["cd"]  # engine precedence: cd replaces unk (vcd_sample.py:148)
@@ -224,7 +241,7 @@ class LlavaLlamaForCausalLM:
             ss_buf = torch.empty(len(stream_names), B, V, dtype=torch.float32, device=self.device)
         new_tokens, steps = self.engine.generate(input_ids, images if has_image else None, use_unk, use_none, params,
                                                  max_new_tokens, q, scores_buf, images_cd if (vdd and use_cd) else None, attn_buf, ss_buf,
-                                                 ragged)
+                                                 ragged, attn_all)
         if gen is not None:
             gen.set_offset(offset + self.engine.sampler_rng_advance())
         seq = torch.cat([input_ids.to("cpu", torch.int64), new_tokens], dim=1).to(input_ids.device)
@@ -234,8 +251,15 @@ class LlavaLlamaForCausalLM:
         out["scores"] = tuple(scores_buf[i] for i in range(steps)) if want_scores else None
         # vcd_sample.py:241-246: decoder_attentions of the MAIN stream, one entry per step
         L = self.vdd_config.num_hidden_layers
-        out["attentions"] = (tuple(_StepAttentions(i, L, attn_buf if i == 0 else None) for i in range(steps))
-                             if attn_buf is not None else None)
+        if attn_all is not None:
+            # HF's shape: step 0 -> L tensors [B, heads, len, len]; step s -> L tensors [B, heads, 1, len + s]
+            a0, an = attn_all
+            Tm = a0.shape[-1]
+            out["attentions"] = tuple(tuple(a0[l] for l in range(L)) if i == 0 else
+                                      tuple(an[i - 1, l, :, :, None, :Tm + i] for l in range(L)) for i in range(steps))
+        else:
+            out["attentions"] = (tuple(_StepAttentions(i, L, attn_buf if i == 0 else None) for i in range(steps))
+                                 if attn_buf is not None else None)
         out["hidden_states"] = None
         if ss_buf is not None:
             out["stream_scores"] = {n: ss_buf[i] for i, n in enumerate(stream_names)}

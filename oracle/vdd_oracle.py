@@ -227,6 +227,28 @@ class OracleVDD:
         return out.attentions[-1].float()
 
     @torch.no_grad()
+    def all_attentions(self, input_ids, new_tokens, images=None):
+        """`attentions[step]` for every step of the reference's generate(output_attentions=True) (vcd_sample.py:241-246 appends the
+        MAIN stream's `outputs.attentions` each step): step 0 is the prefill, [L, B, heads, len, len]; step s >= 1 is the forward
+        of generated token s-1 over the main KV cache, [L, B, heads, 1, len + s].  `new_tokens` [B, n] are the tokens the run
+        produced (the maps do not depend on how they were sampled).  Deep copy for the same reason as first_step_attention."""
+        import copy
+        from transformers.cache_utils import DynamicCache
+        llama = copy.deepcopy(self.llama)
+        cache = DynamicCache()
+        if images is not None:
+            feats = encode_images(self.vision, self.projector, images, self.cfg.mm_vision_select_layer)
+            out = llama(inputs_embeds=splice_main(llama.model.embed_tokens, input_ids, feats.to(self.dtype)), past_key_values=cache,
+                        use_cache=True, output_attentions=True)
+        else:
+            out = llama(input_ids=input_ids, past_key_values=cache, use_cache=True, output_attentions=True)
+        steps = [torch.stack([a.float() for a in out.attentions], dim=0)]
+        for s in range(1, new_tokens.shape[1]):
+            out = llama(input_ids=new_tokens[:, s - 1:s], past_key_values=cache, use_cache=True, output_attentions=True)
+            steps.append(torch.stack([a.float() for a in out.attentions], dim=0))
+        return steps
+
+    @torch.no_grad()
     def generate(self, input_ids, images=None, images_cd=None, use_dd=False, use_dd_unk=False, cd_alpha=None, cd_beta=None,
                  temperature=None, top_k=None, top_p=None, max_new_tokens=16, do_sample=True,
                  output_scores=False, keep_stream_logits=False, q_list=None, eos_token_id="cfg",

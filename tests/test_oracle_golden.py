@@ -49,6 +49,31 @@ def test_oracle_first_step_attention_matches_reference(case):
     assert np.all(np.triu(got[0, 0], 1) == 0)  # causal: nothing above the diagonal
 
 
+def _attn_golden():
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return json.load(open(os.path.join(here, "ref_tiny_attn.json"))), np.load(os.path.join(here, "ref_tiny_attn.npz"))
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in _attn_golden()[0]["cases"]])
+def test_oracle_all_attentions_match_reference(name):
+    """attentions[step][layer] for EVERY step and layer (vcd_sample.py:241-246) as the unmodified reference returned them
+    (tests/golden/make_attn_golden.py): the oracle's teacher-forced replay of the main stream reproduces them."""
+    meta, data = _attn_golden()
+    case = next(c for c in META["cases"] if c["name"] == name)
+    cfg, sd, oracle = tiny_model(META["weight_seed"])
+    ids, img = make_inputs(cfg, case["B"], case["T"], case["input_seed"])
+    new_tokens = torch.from_numpy(DATA[name + ".sequences"])[:, case["T"]:]
+    got = oracle.all_attentions(ids, new_tokens, img)
+    assert len(got) == case["n_new"]
+    len0 = case["T"] + cfg.num_patches - 1
+    for s, g in enumerate(got):
+        ref = data[f"{name}.s{s}"]
+        assert g.shape == ref.shape == (cfg.num_hidden_layers, case["B"], cfg.num_attention_heads, len0 if s == 0 else 1, len0 + s)
+        np.testing.assert_allclose(g.numpy(), ref, rtol=1e-5, atol=1e-6)
+
+
 def test_multinomial_is_exponential_race():
     """Appendix A Q6: torch.multinomial(p,1) == argmax(p / Exp(1)) drawn from the same generator state.
     The CUDA sampler relies on it: it receives q from torch and returns argmax(p/q)."""
