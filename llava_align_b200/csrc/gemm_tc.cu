@@ -228,9 +228,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // Prefill / ViT / projector GEMMs (M > 128 rows): the 128x128 tile above reads 8 KB of shared memory per UMMA of 64 clocks --
 // exactly the 128 B/clk an SM can deliver -- and measured 38-52 % tensor-pipe activity (profiles/r1_ncu_prefill.json).  Here a
 // tile is 128 x 256 (UMMA 128x256x16: 12 KB per 128 clocks = 96 B/clk), CTAs are persistent (one per SM) and walk the tiles
-// m-fastest so the 6 M-tiles of a weight tile hit it in L2, and the fp32 accumulator is double-buffered in TMEM (2 x 256
+// in groups (gemm_tile_coords below) so that concurrently running CTAs share operand panels in L2, and the fp32 accumulator is double-buffered in TMEM (2 x 256
 // columns) so the four epilogue warps drain tile i while the tensor core works on tile i+1.
 constexpr int GW_BN = 256, GW_STAGES = 4;
+// Persistent tile walk, grouped: GROUP m-tiles x all n-tiles at a time, m fastest inside the group.  The CTAs working at the same
+// moment then share GROUP A panels and (CTAs / GROUP) B panels instead of one B panel and as many A panels as there are CTAs --
+// with 24 512 prefill rows (BASELINE configs[2]) the plain m-fastest walk re-read all of A (200 MB, more than L2) once per n-tile:
+// ~9.6 GB of DRAM traffic for the qkv projection, 4 TB/s, i.e. a DRAM-bound GEMM.  Small M (fewer m-tiles than GROUP) degenerates
+// to the m-fastest walk.
+constexpr int GEMM_TILE_GROUP = 16;
+__device__ __forceinline__ void gemm_tile_coords(int tile, int m_tiles, int n_tiles, int& m_idx, int& n_idx) {
+  const int per_group = GEMM_TILE_GROUP * n_tiles;
+  const int g = tile / per_group, r = tile - g * per_group;
+  const int first_m = g * GEMM_TILE_GROUP;
+  const int gm = min(GEMM_TILE_GROUP, m_tiles - first_m);
+  n_idx = r / gm;
+  m_idx = first_m + (r - n_idx * gm);
+}
 constexpr int GW_STAGE_BYTES = (GM_BM + GW_BN) * GM_BK * 2;  // 48 KB
 constexpr int GW_SMEM = GW_STAGES * GW_STAGE_BYTES + 1024 + 256;
 
@@ -274,7 +288,9 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int gi = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * GM_BM, n0 = (tile / m_tiles) * GW_BN;
+        int mi, ni;
+        gemm_tile_coords(tile, m_tiles, n_tiles, mi, ni);
+        const int m0 = mi * GM_BM, n0 = ni * GW_BN;
         for (int kb = 0; kb < nkb; ++kb, ++gi) {
           const int s = gi % GW_STAGES;
           mbar_wait(&empty_bar[s], ((gi / GW_STAGES) & 1) ^ 1);
@@ -313,7 +329,9 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int quad = warp & 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile % m_tiles) * GM_BM, n0 = (tile / m_tiles) * GW_BN;
+      int mi, ni;
+      gemm_tile_coords(tile, m_tiles, n_tiles, mi, ni);
+      const int m0 = mi * GM_BM, n0 = ni * GW_BN;
       const int buf = it & 1;
       const int row = m0 + quad * 32 + lane;
       int64_t orow = -1;
@@ -352,6 +370,186 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair variant
+// Large prefill GEMMs (at least one wave of 256x256 tiles over the 74 SM pairs): the 128x256 kernel above is bound by shared-memory
+// bandwidth -- per UMMA of 128 clocks an SM reads 12 KB of operands and TMA writes 12 KB of the next ones, 192 B/clk against the
+// 128 B/clk an SM has -- and measured 1030-1170 TFLOP/s (profiles/r2_launch_list_config2_prefill.json).  Here two CTAs of one
+// cluster (the two SMs of a TPC) share a 256x256 tile through tcgen05.mma.cta_group::2: CTA r stages rows [128r, 128r+128) of A
+// and rows [128r, 128r+128) of the B tile (8 KB + 8 KB per UMMA instead of 12 + 12), the LEADER CTA's single thread issues the
+// UMMA 256x256x16 for both, and each CTA's TMEM receives the accumulator of its own 128 rows.  Barriers: both CTAs' TMA loads
+// complete_tx on the leader's `full` barrier; the leader's tcgen05.commit multicasts `empty` / `tmem full` to both CTAs; the
+// epilogue warps of both CTAs arrive on the leader's `tmem empty` barrier.  Everything else (persistent m-fastest tile walk, TMEM
+// double buffer, fused epilogues) is the wide kernel's.
+constexpr int GP_BM = 256, GP_BN = 256, GP_STAGES = 6;
+constexpr int GP_STAGE_BYTES = (GM_BM + GP_BN / 2) * GM_BK * 2;  // 32 KB per CTA
+constexpr int GP_SMEM = GP_STAGES * GP_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmEpi ep,
+                    int m_tiles, int n_tiles) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GP_STAGES * GP_STAGE_BYTES);  // the leader's are the ones in use
+  uint64_t* empty_bar = full_bar + GP_STAGES;
+  uint64_t* tfull_bar = empty_bar + GP_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;                                                 // the leader's are the ones in use
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nkb = (ep.K + GM_BK - 1) / GM_BK;
+  const int tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < GP_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 8);  // four epilogue warps of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {  // one warp of EACH CTA, same shared-memory slot: the allocation is collective over the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // the peer's barriers exist before anything signals them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int gi = 0;
+      for (int tile = pair; tile < tiles; tile += npairs) {
+        int mi, ni;
+        gemm_tile_coords(tile, m_tiles, n_tiles, mi, ni);
+        const int m0 = mi * GP_BM + (int)rank * GM_BM, n0 = ni * GP_BN + (int)rank * (GP_BN / 2);
+        for (int kb = 0; kb < nkb; ++kb, ++gi) {
+          const int s = gi % GP_STAGES;
+          mbar_wait(&empty_bar[s], ((gi / GP_STAGES) & 1) ^ 1);
+          unsigned char* sa = smem + s * GP_STAGE_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * GP_STAGE_BYTES);  // both CTAs' bytes land on the leader's barrier
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+          tma_load_2d_pair(sa, &tmap_a, fb, kb * GM_BK, m0);
+          tma_load_2d_pair(sa + GM_BM * GM_BK * 2, &tmap_b, fb, kb * GM_BK, n0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GP_BM, GP_BN);
+      int gi = 0, it = 0;
+      for (int tile = pair; tile < tiles; tile += npairs, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)buf * GP_BN;
+        for (int kb = 0; kb < nkb; ++kb, ++gi) {
+          const int s = gi % GP_STAGES;
+          mbar_wait(&full_bar[s], (gi / GP_STAGES) & 1);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * GP_STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + GM_BM * GM_BK * 2);
+#pragma unroll
+          for (int k = 0; k < GM_BK / 16; ++k) umma_bf16_pair(acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[s]);
+        }
+        umma_commit_pair(&tfull_bar[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    int it = 0;
+    for (int tile = pair; tile < tiles; tile += npairs, ++it) {
+      int mi, ni;
+      gemm_tile_coords(tile, m_tiles, n_tiles, mi, ni);
+      const int m0 = mi * GP_BM + (int)rank * GM_BM, n0 = ni * GP_BN;
+      const int buf = it & 1;
+      const int row = m0 + quad * 32 + lane;
+      int64_t orow = -1;
+      if (row < ep.M) orow = ep.row_map ? ep.row_map[row] : row;
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < GP_BN / 16; c += 2) {
+        uint32_t r0[16], r1[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * GP_BN + c * 16;
+        tmem_ld16(ta, r0);
+        tmem_ld16(ta + 16, r1);
+        tmem_ld_wait();
+        const int col = n0 + c * 16;
+        if (orow >= 0 && col < ep.N) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
+          gm_store16(ep, orow, col, v, 0);
+        }
+        if (orow >= 0 && col + 16 < ep.N) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
+          gm_store16(ep, orow, col + 16, v, 0);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // neither CTA leaves (or frees TMEM) while its peer can still signal its barriers or read its operands
+  gm_tp_arrive(ep);
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -374,6 +572,7 @@ static bool gemm_init() {
   e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gm_smem(3));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_MAX);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GW_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_SMEM);
   if (e != cudaSuccess) {
     g_init_err = "cudaFuncSetAttribute(gemm_tc_kernel) failed";
     g_encode = nullptr;
@@ -444,6 +643,25 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   static const bool shallow_only = getenv("VDD_GEMM_SHALLOW") != nullptr, fixed_bn = getenv("VDD_GEMM_BN128") != nullptr,
                     no_wide = getenv("VDD_GEMM_NARROW") != nullptr;
+  static const bool no_pair = getenv("VDD_GEMM_NO_PAIR") != nullptr;
+  const int pair_m = (a.M + GP_BM - 1) / GP_BM, pair_n = (a.N + GP_BN - 1) / GP_BN;
+  if (a.M > GM_BM && !no_pair && !no_wide && !shallow_only && ep.splits == 1 && (num_sms % 2) == 0 && pair_m * pair_n >= num_sms / 2) {
+    // at least one wave of 256x256 tiles over the SM pairs: cta_group::2
+    ep.bn = GP_BN;
+    ep.stages = GP_STAGES;
+    if (!make_tmap(&ta, a.a, a.M, a.K) || !make_tmap(&tb, a.w, a.N, a.K, GP_BN / 2)) return cudaErrorInvalidValue;
+    cfg.gridDim = dim3(num_sms);  // 74 clusters of 2 (the kernel carries __cluster_dims__(2, 1, 1))
+    cfg.dynamicSmemBytes = GP_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute atp[1];
+    atp[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    atp[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = atp;
+    cfg.numAttrs = a.pdl ? 1 : 0;
+    if (a.defer_reduce) *a.defer_reduce = 0;
+    if (a.tp_ctas) *a.tp_ctas = (int)cfg.gridDim.x;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel, ta, tb, ep, pair_m, pair_n);
+  }
   const int wide_tiles = ((a.M + GM_BM - 1) / GM_BM) * ((a.N + GW_BN - 1) / GW_BN);
   if (a.M > GM_BM && ep.splits == 1 && !no_wide && !shallow_only && wide_tiles >= num_sms) {
     // GEMM-shaped work (prefill of all streams, ViT, projector): persistent 128x256 tiles, TMEM double buffer.  Problems with

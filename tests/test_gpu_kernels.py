@@ -192,9 +192,12 @@ def test_gemv_rmsnorm_swiglu(R):
 # ------------------------------------------------------------------------------------------------ tcgen05 GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (670, 768, 256), (300, 384, 1376), (1154, 1024, 640), (96, 4096, 4096),
                                    (5, 512, 128),
-                                   # at least one wave of 128x256 tiles -> the persistent wide variant (TMEM double buffer),
-                                   # incl. N off the 256 tile and several tiles per CTA
-                                   (1300, 4096, 512), (2000, 3088, 320), (670, 12288, 4096)])
+                                   # at least one wave of 256x256 tiles over the SM pairs -> the persistent cta_group::2 variant (TMEM
+                                   # double buffer), incl. N off the 256 tile and several tiles per pair
+                                   (1300, 4096, 512), (2000, 3088, 320), (670, 12288, 4096),
+                                   # cta_group::2 pair kernel (>= 74 tiles of 256x256): more m-tiles than one raster group (16) with a
+                                   # short last group, and M between one and two CTA row blocks (the second CTA of the pair mostly empty)
+                                   (5000, 1024, 256), (200, 22016, 512)])
 def test_gemm_epilogues(M, N, K):
     L = _lib()
     lib = L.load()

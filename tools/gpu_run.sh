@@ -1,2 +1,10 @@
-# full attention capture: engine tests that touch attentions + driver shim
-timeout 900 python -m pytest tests/test_gpu_engine.py tests/test_driver_shim.py -m gpu -q -k "attention or attentions or shim or calibrate or driver" > gpurun_out/r2t_attn.log 2>&1; echo "rc=$?"; tail -30 gpurun_out/r2t_attn.log
+# cta_group::2 pair GEMM: kernel tests, then the stack tests + bench if they pass
+timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "gemm" > gpurun_out/r2u_gemm.log 2>&1; rc=$?
+echo "gemm tests rc=$rc"; tail -25 gpurun_out/r2u_gemm.log
+if [ $rc -eq 0 ]; then
+  timeout 900 python -m pytest tests/test_gpu_realwidth.py tests/test_gpu_fullsize.py -m gpu -q > gpurun_out/r2u_stack.log 2>&1; echo "stack rc=$?"; tail -5 gpurun_out/r2u_stack.log
+  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2u_bench.json 2> gpurun_out/r2u_bench.err; echo "bench rc=$?"
+  python -c "
+import json;d=json.loads(open('gpurun_out/r2u_bench.json').read())
+print(round(d['value'],1), d['decode_step']); c=d['configs']['configs[2]']; print(round(c['value'],1), c['decode_step'])"
+fi
