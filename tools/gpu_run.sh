@@ -1,10 +1,8 @@
-# cta_group::2 pair GEMM: kernel tests, then the stack tests + bench if they pass
-timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "gemm" > gpurun_out/r2u_gemm.log 2>&1; rc=$?
-echo "gemm tests rc=$rc"; tail -25 gpurun_out/r2u_gemm.log
-if [ $rc -eq 0 ]; then
-  timeout 900 python -m pytest tests/test_gpu_realwidth.py tests/test_gpu_fullsize.py -m gpu -q > gpurun_out/r2u_stack.log 2>&1; echo "stack rc=$?"; tail -5 gpurun_out/r2u_stack.log
-  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2u_bench.json 2> gpurun_out/r2u_bench.err; echo "bench rc=$?"
-  python -c "
-import json;d=json.loads(open('gpurun_out/r2u_bench.json').read())
-print(round(d['value'],1), d['decode_step']); c=d['configs']['configs[2]']; print(round(c['value'],1), c['decode_step'])"
-fi
+# launch list of one configs[2]-shape prefill with the pair GEMM, then ncu --set full of one pair GEMM and one attention launch
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2v_prefill_launches.csv \
+  python bench.py --profile --batch 32 --prompt-len 64 --new-tokens 2 --steps 1 --warmup 0 --no-configs > gpurun_out/r2v.log 2>&1; echo "ncu list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_pair_kernel -s 120 -c 2 -o gpurun_out/r2v_pair_gemm -f \
+  python bench.py --profile --batch 32 --prompt-len 64 --new-tokens 2 --steps 1 --warmup 0 --no-configs > gpurun_out/r2v2.log 2>&1; echo "ncu pair rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:prefill_attn_tc_kernel -s 30 -c 1 -o gpurun_out/r2v_fa -f \
+  python bench.py --profile --batch 32 --prompt-len 64 --new-tokens 2 --steps 1 --warmup 0 --no-configs > gpurun_out/r2v3.log 2>&1; echo "ncu fa rc=$?"
+ls -la gpurun_out/*.ncu-rep
