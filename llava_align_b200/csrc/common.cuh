@@ -20,6 +20,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// rotate-half RoPE of the pair (x1 = x[i], x2 = x[i + 64]) with explicit roundings, so that every prefill site (the projection's
+// fused epilogue and the separate pass) produces the same bits regardless of how the compiler would contract a*b - c*d
+__device__ __forceinline__ float rope_first(float x1, float x2, float c, float s) { return __fmaf_rn(x1, c, -__fmul_rn(x2, s)); }
+__device__ __forceinline__ float rope_second(float x1, float x2, float c, float s) { return __fmaf_rn(x2, c, __fmul_rn(x1, s)); }
+
 // ---------------------------------------------------------------- warp / block reductions (fixed order => deterministic)
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(128) rope_kv_prefill_kernel(const float* __res
   const float* base = qkv + (size_t)row * 3 * Hl + h * D;
   const float q1 = base[i], q2 = base[i + 64];
   const float k1 = base[Hl + i], k2 = base[Hl + i + 64];
-  const float qr = tid < 64 ? (q1 * c - q2 * s) : (q2 * c + q1 * s);
-  const float kr = tid < 64 ? (k1 * c - k2 * s) : (k2 * c + k1 * s);
+  const float qr = tid < 64 ? rope_first(q1, q2, c, s) : rope_second(q1, q2, c, s);
+  const float kr = tid < 64 ? rope_first(k1, k2, c, s) : rope_second(k1, k2, c, s);
   q_out[(size_t)row * Hl + h * D + tid] = __float2bfloat16_rn(qr);
   const size_t o = kv_off[seq] + ((size_t)h * kv_cap[seq] + pos) * D + tid;
   kc[o] = __float2bfloat16_rn(kr);

@@ -700,7 +700,7 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
   // ---- buffers
   RC(ensure(e, e->resid, (size_t)Mtot * H * 4));
   RC(ensure(e, e->xn, (size_t)Mtot * H * 2));
-  RC(ensure(e, e->qkv, (size_t)Mtot * 3 * Hl * 4));
+  if (!gemm_qkv_rope_fused(Mtot, 3 * Hl, H)) RC(ensure(e, e->qkv, (size_t)Mtot * 3 * Hl * 4));  // fp32 projection output (unfused RoPE)
   RC(ensure(e, e->qb, (size_t)Mtot * Hl * 2));
   RC(ensure(e, e->attn, (size_t)Mtot * Hl * 2));
   RC(ensure(e, e->hbuf, (size_t)Mtot * Il * 2));
@@ -788,9 +788,17 @@ static int prefill_impl(vdd_engine* e, const int64_t* ids, int B, int T, int wit
     void* kc = kbase + (size_t)l * kv_total;
     void* vc = kbase + (size_t)(L + l) * kv_total;
     LK(e, launch_rmsnorm_bf16(resid, w.ln1, c.rms_eps, e->xn.p, Mtot, H, nullptr, st));
-    RC(do_gemm(e, e->xn.p, w.wqkv, Mtot, 3 * Hl, H, GEMM_OUT_F32, nullptr, nullptr, (float*)e->qkv.p, nullptr, 3 * Hl, st));
-    LK(e, launch_rope_kv_prefill((const float*)e->qkv.p, Mtot, e->heads_l, 128, e->d_row_seq, e->d_row_pos, e->d_kv_off, e->d_kv_cap,
-                                 e->rope_cos, e->rope_sin, e->qb.p, kc, vc, st));
+    if (gemm_qkv_rope_fused(Mtot, 3 * Hl, H)) {
+      // RoPE, the bf16 casts and the KV-cache scatter ride in the projection's epilogue: no fp32 [Mtot, 3*Hl] round trip
+      QkvRopeEpi qr{e->d_row_seq, e->d_row_pos, e->d_kv_off, e->d_kv_cap, e->rope_cos, e->rope_sin, e->qb.p, kc, vc, Hl};
+      GemmArgs g{e->xn.p, w.wqkv, Mtot, 3 * Hl, H, GEMM_OUT_QKV_ROPE, nullptr, nullptr, nullptr, nullptr, 3 * Hl};
+      g.qkv_rope = &qr;
+      LK(e, launch_gemm(g, st));
+    } else {
+      RC(do_gemm(e, e->xn.p, w.wqkv, Mtot, 3 * Hl, H, GEMM_OUT_F32, nullptr, nullptr, (float*)e->qkv.p, nullptr, 3 * Hl, st));
+      LK(e, launch_rope_kv_prefill((const float*)e->qkv.p, Mtot, e->heads_l, 128, e->d_row_seq, e->d_row_pos, e->d_kv_off, e->d_kv_cap,
+                                   e->rope_cos, e->rope_sin, e->qb.p, kc, vc, st));
+    }
     PrefillAttnArgs pa{};
     pa.q = e->qb.p; pa.q_ld = Hl; pa.k = kc; pa.v = vc; pa.k_off = e->d_kv_off; pa.k_head_stride = e->d_head_stride;
     pa.k_tok_stride = 128; pa.q_row0 = e->d_q_row0; pa.seqlen = e->d_seqlen; pa.out = e->attn.p; pa.out_ld = Hl;

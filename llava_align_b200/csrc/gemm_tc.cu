@@ -41,6 +41,7 @@ struct GemmEpi {
   float* out_f32;
   __nv_bfloat16* out_bf16;
   int64_t ldc;
+  QkvRopeEpi rope;      // GEMM_OUT_QKV_ROPE
   int tp;               // > 1: GEMM_OUT_F32 tiles go to every rank (peer memory over NVLink) and every CTA signals every rank
   float* tp_out[8];
   unsigned* tp_cnt[8];
@@ -107,6 +108,58 @@ __device__ __forceinline__ void gm_store16(const GemmEpi& ep, int64_t orow, int 
     uint4* o = reinterpret_cast<uint4*>(ep.out_bf16 + orow * ep.ldc + col);
     o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// GEMM_OUT_QKV_ROPE epilogue of one row of a 256-column tile (= two heads of ONE of the q / k / v sections; Hl % 256 == 0):
+// rotate-half pairs (d, d + 64) are four 16-column chunks apart in TMEM.  fp32 in, the same arithmetic as rope_kv_prefill_kernel.
+__device__ __forceinline__ void gm_qkv_rope_row(const QkvRopeEpi& r, uint32_t tmem_row, int row, int n0, bool store) {
+  const int sec = n0 / r.Hl, h0 = (n0 - sec * r.Hl) >> 7;
+  const int seq = r.row_seq[row], pos = r.row_pos[row];
+  const float* cs = r.rope_cos + (size_t)pos * 64;
+  const float* sn = r.rope_sin + (size_t)pos * 64;
+#pragma unroll 1
+  for (int hh = 0; hh < 2; ++hh) {
+    __nv_bfloat16* dst;
+    if (sec == 0) dst = reinterpret_cast<__nv_bfloat16*>(r.q_out) + (size_t)row * r.Hl + (h0 + hh) * 128;
+    else dst = reinterpret_cast<__nv_bfloat16*>(sec == 1 ? r.kc : r.vc) + r.kv_off[seq] + ((size_t)(h0 + hh) * r.kv_cap[seq] + pos) * 128;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t a[16], b[16];
+      tmem_ld16(tmem_row + hh * 128 + cc * 16, a);
+      tmem_ld16(tmem_row + hh * 128 + 64 + cc * 16, b);
+      tmem_ld_wait();
+      uint32_t lo[8], hi[8];
+      if (sec < 2) {
+        float c[16], s[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cs + cc * 16 + 4 * i), s4 = *reinterpret_cast<const float4*>(sn + cc * 16 + 4 * i);
+          c[4 * i] = c4.x; c[4 * i + 1] = c4.y; c[4 * i + 2] = c4.z; c[4 * i + 3] = c4.w;
+          s[4 * i] = s4.x; s[4 * i + 1] = s4.y; s[4 * i + 2] = s4.z; s[4 * i + 3] = s4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x1a = __uint_as_float(a[2 * i]), x1b = __uint_as_float(a[2 * i + 1]);
+          const float x2a = __uint_as_float(b[2 * i]), x2b = __uint_as_float(b[2 * i + 1]);
+          lo[i] = pack_bf16(rope_first(x1a, x2a, c[2 * i], s[2 * i]), rope_first(x1b, x2b, c[2 * i + 1], s[2 * i + 1]));
+          hi[i] = pack_bf16(rope_second(x1a, x2a, c[2 * i], s[2 * i]), rope_second(x1b, x2b, c[2 * i + 1], s[2 * i + 1]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          lo[i] = pack_bf16(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1]));
+          hi[i] = pack_bf16(__uint_as_float(b[2 * i]), __uint_as_float(b[2 * i + 1]));
+        }
+      }
+      if (!store) continue;
+      uint4* d0 = reinterpret_cast<uint4*>(dst + cc * 16);
+      uint4* d1 = reinterpret_cast<uint4*>(dst + 64 + cc * 16);
+      d0[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      d0[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      d1[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      d1[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    }
   }
 }
 
@@ -518,6 +571,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (row < ep.M) orow = ep.row_map ? ep.row_map[row] : row;
       mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
       tcgen05_fence_after();
+      if (ep.mode == GEMM_OUT_QKV_ROPE) {
+        // every lane runs the (warp-collective) TMEM loads; lanes past M read row M-1's metadata and store nothing
+        gm_qkv_rope_row(ep.rope, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * GP_BN, min(row, ep.M - 1), n0, row < ep.M);
+      } else
 #pragma unroll 1
       for (int c = 0; c < GP_BN / 16; c += 2) {
         uint32_t r0[16], r1[16];
@@ -604,6 +661,22 @@ bool make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t co
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static bool gemm_uses_pair_kernel(int M, int N) {
+  static const bool off = getenv("VDD_GEMM_NO_PAIR") != nullptr || getenv("VDD_GEMM_NARROW") != nullptr || getenv("VDD_GEMM_SHALLOW") != nullptr;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int pair_m = (M + GP_BM - 1) / GP_BM, pair_n = (N + GP_BN - 1) / GP_BN;
+  return !off && M > GM_BM && (num_sms % 2) == 0 && pair_m * pair_n >= num_sms / 2;
+}
+bool gemm_qkv_rope_fused(int M, int N, int K) {
+  static const bool off = getenv("VDD_NO_ROPE_FUSION") != nullptr;
+  return !off && gemm_init() && gemm_uses_pair_kernel(M, N) && N % (3 * GP_BN) == 0 && K % 8 == 0;
+}
+
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (!gemm_init()) return cudaErrorNotSupported;
   if (a.M <= 0) return cudaSuccess;
@@ -643,9 +716,13 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   }
   static const bool shallow_only = getenv("VDD_GEMM_SHALLOW") != nullptr, fixed_bn = getenv("VDD_GEMM_BN128") != nullptr,
                     no_wide = getenv("VDD_GEMM_NARROW") != nullptr;
-  static const bool no_pair = getenv("VDD_GEMM_NO_PAIR") != nullptr;
   const int pair_m = (a.M + GP_BM - 1) / GP_BM, pair_n = (a.N + GP_BN - 1) / GP_BN;
-  if (a.M > GM_BM && !no_pair && !no_wide && !shallow_only && ep.splits == 1 && (num_sms % 2) == 0 && pair_m * pair_n >= num_sms / 2) {
+  const bool use_pair = gemm_uses_pair_kernel(a.M, a.N) && ep.splits == 1;
+  if (a.epilogue == GEMM_OUT_QKV_ROPE) {
+    if (!use_pair || !a.qkv_rope || a.qkv_rope->Hl % GP_BN || a.N != 3 * a.qkv_rope->Hl || a.bias || a.row_map || ep.tp) return cudaErrorInvalidValue;
+    ep.rope = *a.qkv_rope;
+  }
+  if (use_pair) {
     // at least one wave of 256x256 tiles over the SM pairs: cta_group::2
     ep.bn = GP_BN;
     ep.stages = GP_STAGES;

@@ -136,7 +136,20 @@ enum GemmEpilogue {
   GEMM_OUT_BF16 = 2,       // out_bf16 = acc (+bias)
   GEMM_OUT_BF16_QGELU = 3, // quick_gelu(acc+bias)   (CLIP MLP)
   GEMM_OUT_BF16_GELU = 4,  // gelu_erf(acc+bias)     (mm_projector)
-  GEMM_OUT_SWIGLU = 5      // out_bf16[row, col/2] = silu(acc[2i]) * acc[2i+1]  (interleaved gate/up)
+  GEMM_OUT_SWIGLU = 5,     // out_bf16[row, col/2] = silu(acc[2i]) * acc[2i+1]  (interleaved gate/up)
+  GEMM_OUT_QKV_ROPE = 6    // prefill qkv: RoPE + bf16 q / KV-cache writes in the epilogue (GemmArgs::qkv_rope; SM-pair kernel only)
+};
+struct QkvRopeEpi {
+  const int32_t* row_seq;  // [M] sequence of the row
+  const int32_t* row_pos;  // [M] position of the row inside its sequence
+  const int64_t* kv_off;   // [nseq] element offset of the sequence's block in a cache layer
+  const int32_t* kv_cap;   // [nseq]
+  const float* rope_cos;   // [max_pos, 64]
+  const float* rope_sin;
+  void* q_out;             // bf16 [M, Hl]
+  void* kc;                // bf16 K cache of the layer: (seq, head h, token t) at kc + kv_off[seq] + (h*kv_cap[seq] + t)*128
+  void* vc;
+  int Hl;                  // heads_local * 128, a multiple of 256
 };
 struct GemmArgs {
   const void* a;  // bf16 [M, K] row-major (lda = K)
@@ -161,8 +174,14 @@ struct GemmArgs {
   float* tp_out[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned* tp_cnt[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int* tp_ctas = nullptr;       // out: CTAs of the launch (arrivals this rank contributes per peer)
+  // GEMM_OUT_QKV_ROPE (prefill qkv projection, N = 3*Hl, head_dim 128): the epilogue ropes q and k in fp32 and writes q bf16 to
+  // [M, Hl], k / v bf16 into the head-major KV cache of the row's sequence -- no fp32 [M, 3*Hl] round trip, no separate pass
+  const QkvRopeEpi* qkv_rope = nullptr;
 };
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
+// true when launch_gemm would run GEMM_OUT_QKV_ROPE for this shape (the SM-pair kernel); otherwise the caller keeps the fp32
+// projection + launch_rope_kv_prefill
+bool gemm_qkv_rope_fused(int M, int N, int K);
 const char* gemm_init_error();
 
 // ---------------------------------------------------------------- attention

@@ -87,3 +87,47 @@ def test_7b_width_96_rows_tensor_core_decode(model7b_2layers):
 def test_13b_width_two_rows():
     cfg, m, oracle = _model("llava-v1.5-13b", 2)
     _check(cfg, m, oracle, 1, True, False, 4)
+
+
+_CHILD = r"""
+import dataclasses, sys, torch
+sys.path.insert(0, {repo!r}); sys.path.insert(0, {tests!r})
+from llava_align_b200.config import by_name
+from llava_align_b200.model import LlavaLlamaForCausalLM, evolve_vcd_sampling
+from llava_align_b200.weights import make_state_dict
+from helpers import make_inputs
+cfg = dataclasses.replace(by_name("llava-v1.5-7b"), num_hidden_layers=2, vision_num_hidden_layers=3, name="llava-v1.5-7b@2")
+sd = make_state_dict(cfg, seed=11)
+evolve_vcd_sampling()
+m = LlavaLlamaForCausalLM(cfg, "cuda:0"); m.load_state_dict(sd)
+ids, img = make_inputs(cfg, 2, 32, 9)
+m.engine.encode_images(img)
+lg = m.engine.prefill(ids, True, True, True, 4).clone()
+steps = [lg.cpu()]
+for t in (5, 17):
+    steps.append(m.engine.decode_step(torch.full((2,), t, dtype=torch.int64)).clone().cpu())
+torch.save(steps, {out!r})
+"""
+
+
+def test_fused_rope_epilogue_equals_separate_pass(model7b_2layers, tmp_path):
+    """The qkv projection of a large prefill ropes q / k and scatters k / v into the cache from its epilogue (gemm_tc.cu,
+    GEMM_OUT_QKV_ROPE); a child process with VDD_NO_ROPE_FUSION=1 runs the fp32 projection + rope_kv_prefill_kernel instead.  Same
+    fp32 accumulators, same arithmetic: prefill logits and the logits of two decode steps over the cache it wrote are bit-identical."""
+    import os
+    import subprocess
+    import sys
+    from helpers import make_inputs
+    cfg, m, oracle = model7b_2layers
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "unfused.pt")
+    env = dict(os.environ, VDD_NO_ROPE_FUSION="1")
+    subprocess.run([sys.executable, "-c", _CHILD.format(repo=os.path.dirname(here), tests=here, out=out)], check=True, env=env, timeout=600)
+    ref = torch.load(out)
+    ids, img = make_inputs(cfg, 2, 32, 9)
+    m.engine.encode_images(img)
+    got = [m.engine.prefill(ids, True, True, True, 4).clone().cpu()]
+    for t in (5, 17):
+        got.append(m.engine.decode_step(torch.full((2,), t, dtype=torch.int64)).clone().cpu())
+    for g, r in zip(got, ref):
+        assert torch.equal(g, r), (g - r).abs().max().item()
