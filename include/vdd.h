@@ -10,6 +10,14 @@
  * pointers are DEVICE pointers unless the name ends in _host; all work is enqueued on the caller's stream
  * (a cudaStream_t passed as void*), no hidden synchronisation unless stated; one engine is used from one
  * host thread; tensor-parallel runs use one engine per rank.  No torch types appear here.
+ *
+ * Threading and memory: an engine is NOT thread-safe.  Its work buffers grow on demand inside vdd_prefill* / vdd_generate*
+ * (cudaFree + cudaMalloc of the buffer that is too small); the CUDA graph of the decode step is keyed on every pointer and shape
+ * it bakes in and is re-captured after such a growth, so a caller never sees a stale graph -- but two host threads driving one
+ * engine, or a second stream still running the engine's kernels while the next prefill re-allocates, are outside the contract.
+ * The chained decode kernels synchronise their CTAs with a grid barrier that needs the whole grid resident (checked against the
+ * occupancy calculator at launch); a co-tenant kernel that holds SMs for the whole launch makes the barrier's bounded spin trap
+ * (error return), it does not hang.
  */
 #ifndef VDD_H_
 #define VDD_H_

@@ -557,6 +557,20 @@ cudaError_t launch_gemv_chain(const GemvChain& ch, int num_sms, bool pdl, cudaSt
   }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GV_SMEM_BUDGET);
   if (e != cudaSuccess) return e;
+  if (ch.n > 1) {
+    // The split grid barrier between chained projections needs every CTA of the grid resident at once.  Checked against the
+    // occupancy calculator for this kernel / block / shared-memory combination (once per combination); what it cannot see is another
+    // stream's kernel holding SMs for the whole launch -- the barrier's bounded spin turns that into a trap, not a hang.
+    static int ok_R = 0, ok_threads = 0, ok_grid = 0;
+    static size_t ok_smem = 0;
+    if (!(ok_R == R && ok_threads == nwarps * 32 && ok_smem == smem && ok_grid == grid)) {
+      int per_sm = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem);
+      if (e != cudaSuccess) return e;
+      if (per_sm < 1 || grid > per_sm * num_sms) return cudaErrorCooperativeLaunchTooLarge;
+      ok_R = R; ok_threads = nwarps * 32; ok_smem = smem; ok_grid = grid;
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(nwarps * 32);
