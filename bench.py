@@ -381,9 +381,16 @@ def main():
                                              toks.data_ptr(), reps_c, C.byref(ms_c), eng.stream.cuda_stream), "vdd_bench_combine")
             us = 1e3 * ms_c.value
             nbytes = Bc * V * 4 * 4 + Bc * 8
+            # the same launch as generate() issues it: no q tensor, the variates drawn in-kernel (Philox, torch's stream)
+            _lib.check(lib.vdd_bench_combine(l.data_ptr(), u.data_ptr(), d.data_ptr(), Bc, V, V, C.byref(pc), None,
+                                             toks.data_ptr(), reps_c, C.byref(ms_c), eng.stream.cuda_stream), "vdd_bench_combine")
+            us_p = 1e3 * ms_c.value
+            nbytes_p = Bc * V * 4 * 3 + Bc * 8
             combine.append({"B": Bc, "us_per_launch": us, "GBps": nbytes / us / 1e3, "bytes": nbytes, "frac_of_hbm_peak": nbytes / us / 1e3 / peak,
                             "resident": "L2 (same inputs every replay)" if nbytes < 100e6 else "HBM (inputs larger than L2)",
-                            "how": f"{reps_c} launches in one CUDA graph, best of 3 replays"})
+                            "how": f"{reps_c} launches in one CUDA graph, best of 3 replays",
+                            "in_kernel_variates": {"us_per_launch": us_p, "bytes": nbytes_p, "GBps": nbytes_p / us_p / 1e3,
+                                                   "frac_of_hbm_peak": nbytes_p / us_p / 1e3 / peak}})
         del l, u, d, qq
 
     cpu = None

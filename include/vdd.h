@@ -82,7 +82,8 @@ VDD_API int vdd_logit_combine_sample(const float* l, const float* u, const float
                              int64_t* tokens_out, int32_t* unfinished, void* stream);
 
 /* Measurement aid (bench.py's logit-combine GB/s): `reps` launches of K8 on the same inputs captured in one CUDA graph,
- * replayed four times; *ms_per_launch_out = best replay / reps.  The stream must not be the legacy default stream.       */
+ * replayed four times; *ms_per_launch_out = best replay / reps.  The stream must not be the legacy default stream.  q = NULL: the
+ * variates are drawn inside the kernel (Philox, fixed seed), as vdd_generate* does when no q_exp is passed.                 */
 VDD_API int vdd_bench_combine(const float* l, const float* u, const float* d, int B, int V, int64_t ld,
                       const vdd_sample_params* params_host, const float* q_exp, int64_t* tokens_out, int reps,
                       float* ms_per_launch_out, void* stream);

@@ -1225,6 +1225,16 @@ extern "C" int vdd_bench_combine(const float* l, const float* u, const float* d,
   SampleArgs a{};
   a.l = l; a.u = u; a.d = d; a.q = q; a.tokens_out = tokens_out; a.ld = ld; a.B = B; a.V = V;
   fill_sample_args(a, *p);
+  if (!q) {  // the product path of generate(): the Exp(1) variates come from Philox inside the kernel, no [B, V] read
+    int dev = 0, sms = 0, mt = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&mt, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+    sample_philox_geometry(a, (long long)B * V, sms, mt);
+    a.philox_seed = 0x5eed;
+    a.philox_offset = 0;
+    a.use_philox = 1;
+  }
   cudaGraph_t g = nullptr;
   cudaGraphExec_t ge = nullptr;
   CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
