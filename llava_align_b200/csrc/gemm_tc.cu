@@ -113,13 +113,13 @@ __device__ __forceinline__ void gm_store16(const GemmEpi& ep, int64_t orow, int 
 
 // GEMM_OUT_QKV_ROPE epilogue of one row of a 256-column tile (= two heads of ONE of the q / k / v sections; Hl % 256 == 0):
 // rotate-half pairs (d, d + 64) are four 16-column chunks apart in TMEM.  fp32 in, the same arithmetic as rope_kv_prefill_kernel.
-__device__ __forceinline__ void gm_qkv_rope_row(const QkvRopeEpi& r, uint32_t tmem_row, int row, int n0, bool store) {
+__device__ __forceinline__ void gm_qkv_rope_row(const QkvRopeEpi& r, uint32_t tmem_row, int row, int n0, bool store, int hh0, int hh1) {
   const int sec = n0 / r.Hl, h0 = (n0 - sec * r.Hl) >> 7;
   const int seq = r.row_seq[row], pos = r.row_pos[row];
   const float* cs = r.rope_cos + (size_t)pos * 64;
   const float* sn = r.rope_sin + (size_t)pos * 64;
 #pragma unroll 1
-  for (int hh = 0; hh < 2; ++hh) {
+  for (int hh = hh0; hh < hh1; ++hh) {
     __nv_bfloat16* dst;
     if (sec == 0) dst = reinterpret_cast<__nv_bfloat16*>(r.q_out) + (size_t)row * r.Hl + (h0 + hh) * 128;
     else dst = reinterpret_cast<__nv_bfloat16*>(sec == 1 ? r.kc : r.vc) + r.kv_off[seq] + ((size_t)(h0 + hh) * r.kv_cap[seq] + pos) * 128;
@@ -434,6 +434,10 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // epilogue warps of both CTAs arrive on the leader's `tmem empty` barrier.  Everything else (persistent m-fastest tile walk, TMEM
 // double buffer, fused epilogues) is the wide kernel's.
 constexpr int GP_BM = 256, GP_BN = 256, GP_STAGES = 6;
+// warps: 0 = TMA producer, 1 = TMEM allocator + MMA issuer (leader CTA), 2..9 = epilogue -- TWO warps per TMEM lane quadrant, each
+// draining one 128-column half of the accumulator (with four warps the QuickGELU / SwiGLU / RoPE epilogues of short-K GEMMs, e.g.
+// the ViT's fc1 at K = 1024, took longer than the tile's MMAs and the tensor core waited for a free accumulator)
+constexpr int GP_THREADS = 320, GP_EPI_WARPS = 8;
 constexpr int GP_STAGE_BYTES = (GM_BM + GP_BN / 2) * GM_BK * 2;  // 32 KB per CTA
 constexpr int GP_SMEM = GP_STAGES * GP_STAGE_BYTES + 1024 + 256;
 
@@ -475,7 +479,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GP_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmEpi ep,
                     int m_tiles, int n_tiles) {
   extern __shared__ unsigned char smem_raw[];
@@ -501,7 +505,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 8);  // four epilogue warps of each CTA
+      mbar_init(&tempty_bar[b], 2 * GP_EPI_WARPS);  // the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -559,7 +563,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     __syncwarp();
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3, half = (warp - 2) >> 2;  // TMEM lanes 32*quad.., accumulator columns [128*half, 128*half + 128)
     int it = 0;
     for (int tile = pair; tile < tiles; tile += npairs, ++it) {
       int mi, ni;
@@ -573,10 +577,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tcgen05_fence_after();
       if (ep.mode == GEMM_OUT_QKV_ROPE) {
         // every lane runs the (warp-collective) TMEM loads; lanes past M read row M-1's metadata and store nothing
-        gm_qkv_rope_row(ep.rope, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * GP_BN, min(row, ep.M - 1), n0, row < ep.M);
+        gm_qkv_rope_row(ep.rope, tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * GP_BN, min(row, ep.M - 1), n0, row < ep.M,
+                        half, half + 1);
       } else
 #pragma unroll 1
-      for (int c = 0; c < GP_BN / 16; c += 2) {
+      for (int c = half * (GP_BN / 32); c < (half + 1) * (GP_BN / 32); c += 2) {
         uint32_t r0[16], r1[16];
         const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * GP_BN + c * 16;
         tmem_ld16(ta, r0);
@@ -728,6 +733,7 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     ep.stages = GP_STAGES;
     if (!make_tmap(&ta, a.a, a.M, a.K) || !make_tmap(&tb, a.w, a.N, a.K, GP_BN / 2)) return cudaErrorInvalidValue;
     cfg.gridDim = dim3(num_sms);  // 74 clusters of 2 (the kernel carries __cluster_dims__(2, 1, 1))
+    cfg.blockDim = dim3(GP_THREADS);
     cfg.dynamicSmemBytes = GP_SMEM;
     cfg.stream = stream;
     cudaLaunchAttribute atp[1];
