@@ -1,10 +1,7 @@
-# pair GEMM with eight epilogue warps: kernel tests, real-width stack, bench
-timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "gemm" > gpurun_out/r2B_gemm.log 2>&1; rc=$?
-echo "gemm tests rc=$rc"; tail -3 gpurun_out/r2B_gemm.log
-if [ $rc -eq 0 ]; then
-  timeout 900 python -m pytest tests/test_gpu_realwidth.py tests/test_gpu_engine.py -m gpu -q > gpurun_out/r2B_stack.log 2>&1; echo "stack rc=$?"; tail -3 gpurun_out/r2B_stack.log
-  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2B_bench.json 2> gpurun_out/r2B_bench.err; echo "bench rc=$?"
-  python -c "
-import json;d=json.loads(open('gpurun_out/r2B_bench.json').read())
-print(round(d['value'],1), d['decode_step']); c=d['configs']['configs[2]']; print(round(c['value'],1), c['decode_step'])"
-fi
+# 4-GPU sanity after the prefill rewrite: TP=4 real-width parity + the driver's N=4 bench line
+timeout 900 python -m pytest tests/test_tp_gpu.py -m gpu -q -k "real_width and True-4" > gpurun_out/r2C_tp4_tests.log 2>&1; echo "tp4 tests rc=$?"; grep -E "passed|failed|skipped" gpurun_out/r2C_tp4_tests.log | tail -2
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514"
+timeout 600 $TR bench.py --gpus 4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2C_bench_tp4.json 2> gpurun_out/r2C_bench_tp4.err; echo "bench rc=$?"
+python -c "
+import json;d=json.loads(open('gpurun_out/r2C_bench_tp4.json').read())
+print(round(d['value'],1), d['decode_step'])"
