@@ -137,6 +137,9 @@ VDD_API int vdd_set_sampler_rng(vdd_engine* e, uint64_t seed, uint64_t offset);
 VDD_API uint64_t vdd_sampler_rng_advance(vdd_engine* e);
 /* Test aid: out_dev[i] = element i of `torch.empty(numel, device='cuda').exponential_(1)` under (seed, offset). */
 VDD_API int vdd_debug_philox_exponential(uint64_t seed, uint64_t offset, int64_t numel, float* out_dev, void* stream);
+/* Test aid (host only, no GPU needed): the persistent GEMM kernels' grouped tile walk -- which (m-tile, n-tile) the tile-th unit of
+ * work is.  A bijection onto [0, m_tiles) x [0, n_tiles); consecutive tiles share operand panels (gemm_tc.cu, gemm_tile_coords). */
+VDD_API int vdd_debug_gemm_tile_coords(int tile, int m_tiles, int n_tiles, int* m_idx_host, int* n_idx_host);
 /* Test aid: one launch of the varlen prefill attention (llava_llama.py:91-100 at step 0, clip_encoder.py:48) on caller-provided device
  * buffers.  q is bf16 [q_rows, q_ld]; k / v are bf16 [kv_rows, k_tok_stride]; key t of (sequence s, head h) starts at element
  * k_off[s] + h*k_head_stride[s] + t*k_tok_stride; out is bf16 addressed like q with out_ld.  use_tc: 1 = tcgen05 + TMA kernel, 0 = the

@@ -54,6 +54,7 @@ SIGNATURES = {
     "vdd_set_sampler_rng": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
     "vdd_sampler_rng_advance": (C.c_uint64, [_P]),
     "vdd_debug_philox_exponential": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, _P, _P]),
+    "vdd_debug_gemm_tile_coords": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P]),
     "vdd_debug_prefill_attn": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, C.c_int,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "vdd_set_prompt_mask": (C.c_int, [_P, _P, C.c_int, C.c_int]),

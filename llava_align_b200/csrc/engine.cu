@@ -1122,6 +1122,11 @@ extern "C" int vdd_decode_step(vdd_engine* e, const int64_t* tokens, void* strea
   LK(e, launch_advance(e->d_pos, e->R, nullptr, st, e->d_epoch));  // pos += 1 (and the TP epoch)
   return VDD_OK;
 }
+extern "C" int vdd_debug_gemm_tile_coords(int tile, int m_tiles, int n_tiles, int* m_idx_host, int* n_idx_host) {
+  if (!m_idx_host || !n_idx_host || m_tiles < 1 || n_tiles < 1 || tile < 0 || tile >= m_tiles * n_tiles) return fail(VDD_ERR_ARG, "bad argument");
+  gemm_tile_coords_host(tile, m_tiles, n_tiles, m_idx_host, n_idx_host);
+  return VDD_OK;
+}
 extern "C" int vdd_debug_prefill_attn(const void* q, int64_t q_ld, int64_t q_rows, const void* k, const void* v, int64_t kv_rows,
                                       int64_t k_tok_stride, const int64_t* k_off, const int64_t* k_head_stride, const int32_t* q_row0,
                                       const int32_t* seqlen, void* out, int64_t out_ld, int nseq, int heads, int max_seqlen, int causal,

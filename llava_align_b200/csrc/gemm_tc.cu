@@ -290,11 +290,11 @@ constexpr int GW_BN = 256, GW_STAGES = 4;
 // ~9.6 GB of DRAM traffic for the qkv projection, 4 TB/s, i.e. a DRAM-bound GEMM.  Small M (fewer m-tiles than GROUP) degenerates
 // to the m-fastest walk.
 constexpr int GEMM_TILE_GROUP = 16;
-__device__ __forceinline__ void gemm_tile_coords(int tile, int m_tiles, int n_tiles, int& m_idx, int& n_idx) {
+__host__ __device__ __forceinline__ void gemm_tile_coords(int tile, int m_tiles, int n_tiles, int& m_idx, int& n_idx) {
   const int per_group = GEMM_TILE_GROUP * n_tiles;
   const int g = tile / per_group, r = tile - g * per_group;
   const int first_m = g * GEMM_TILE_GROUP;
-  const int gm = min(GEMM_TILE_GROUP, m_tiles - first_m);
+  const int gm = GEMM_TILE_GROUP < m_tiles - first_m ? GEMM_TILE_GROUP : m_tiles - first_m;
   n_idx = r / gm;
   m_idx = first_m + (r - n_idx * gm);
 }
@@ -677,6 +677,7 @@ static bool gemm_uses_pair_kernel(int M, int N) {
   const int pair_m = (M + GP_BM - 1) / GP_BM, pair_n = (N + GP_BN - 1) / GP_BN;
   return !off && M > GM_BM && (num_sms % 2) == 0 && pair_m * pair_n >= num_sms / 2;
 }
+void gemm_tile_coords_host(int tile, int m_tiles, int n_tiles, int* m_idx, int* n_idx) { gemm_tile_coords(tile, m_tiles, n_tiles, *m_idx, *n_idx); }
 bool gemm_qkv_rope_fused(int M, int N, int K) {
   static const bool off = getenv("VDD_NO_ROPE_FUSION") != nullptr;
   return !off && gemm_init() && gemm_uses_pair_kernel(M, N) && N % (3 * GP_BN) == 0 && K % 8 == 0;

@@ -182,6 +182,8 @@ cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t stream);
 // true when launch_gemm would run GEMM_OUT_QKV_ROPE for this shape (the SM-pair kernel); otherwise the caller keeps the fp32
 // projection + launch_rope_kv_prefill
 bool gemm_qkv_rope_fused(int M, int N, int K);
+// host copy of the persistent kernels' tile walk (tile index -> m-tile, n-tile), for tests
+void gemm_tile_coords_host(int tile, int m_tiles, int n_tiles, int* m_idx, int* n_idx);
 const char* gemm_init_error();
 
 // ---------------------------------------------------------------- attention

@@ -105,3 +105,29 @@ def test_attentions_tuple_serves_only_what_is_materialised():
     for bad in (lambda: a0[0], lambda: a0[2], lambda: a1[-1], lambda: list(a0)):
         with pytest.raises(NotImplementedError):
             bad()
+
+
+@pytest.mark.parametrize("m_tiles,n_tiles", [(3, 48), (96, 48), (96, 86), (20, 4), (1, 86), (17, 1), (16, 5), (33, 7)])
+def test_gemm_tile_walk_is_a_bijection_that_shares_panels(m_tiles, n_tiles):
+    """The persistent tcgen05 GEMMs walk their tiles in groups of 16 m-tiles x all n-tiles (gemm_tc.cu, gemm_tile_coords): every
+    (m, n) tile exactly once, and the 74 tiles in flight at any moment (one per SM pair) touch few distinct operand panels -- with
+    the plain m-fastest walk they touched 74 A panels, which at 24 512 prefill rows made the GEMM DRAM-bound.  Host function."""
+    from llava_align_b200 import _lib
+    lib = _lib.load()
+    seen, order = set(), []
+    m, n = C.c_int(-1), C.c_int(-1)
+    for t in range(m_tiles * n_tiles):
+        assert lib.vdd_debug_gemm_tile_coords(t, m_tiles, n_tiles, C.byref(m), C.byref(n)) == 0
+        assert 0 <= m.value < m_tiles and 0 <= n.value < n_tiles
+        seen.add((m.value, n.value))
+        order.append((m.value, n.value))
+    assert len(seen) == m_tiles * n_tiles
+    assert lib.vdd_debug_gemm_tile_coords(m_tiles * n_tiles, m_tiles, n_tiles, C.byref(m), C.byref(n)) != 0  # out of range
+    wave = 74
+    for t0 in range(0, len(order) - wave + 1, wave):
+        w = order[t0:t0 + wave]
+        panels = len({a for a, _ in w}) + len({b for _, b in w})
+        # a window inside one group of gm m-tiles spans <= gm A panels and ceil(74 / gm) + 1 B panels; one crossing a group boundary
+        # at most twice that (m-fastest over all of M would be min(74, m_tiles) A panels)
+        gm = min(16, m_tiles)
+        assert panels <= 2 * (gm + -(-wave // gm) + 1), (t0, panels)
