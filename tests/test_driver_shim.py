@@ -315,3 +315,22 @@ def test_driver_call_sites_on_the_engine(monkeypatch):
         assert mo['sequences'].shape[1] <= ids2.shape[1] + 6 and mo['scores'][0].shape == (1, cfg.vocab_size)
         assert mo['attentions'][0][-1].shape[-1] == ids2.shape[1]
     _purge()
+
+
+def test_attention_capture_budget(monkeypatch):
+    """output_attentions=True keeps the reference's whole `attentions` tuple (vcd_sample.py:241-246) while it fits the budget and
+    falls back to the one entry the drivers read (`[0][-1]`, llava_calibrate.py:180) beyond it; the environment overrides both."""
+    from llava_align_b200.model import _attention_capture_mode
+    monkeypatch.delenv("VDD_ATTENTIONS", raising=False)
+    monkeypatch.delenv("VDD_ATTENTIONS_MAX_GB", raising=False)
+    # 7B, 607-token prompt after the image splice: 256 new tokens = 2.3 GB -> all; the drivers' max_new_tokens = 1024 = 8.3 GB -> last
+    assert _attention_capture_mode(1, 32, 32, 607, 256) == "all"
+    assert _attention_capture_mode(1, 32, 32, 607, 1024) == "last"
+    assert _attention_capture_mode(32, 32, 32, 639, 64) == "last"      # a POPE batch of 32
+    assert _attention_capture_mode(2, 2, 2, 27, 8) == "all"            # the tiny golden cases
+    monkeypatch.setenv("VDD_ATTENTIONS_MAX_GB", "16")
+    assert _attention_capture_mode(1, 32, 32, 607, 1024) == "all"
+    monkeypatch.setenv("VDD_ATTENTIONS", "last")
+    assert _attention_capture_mode(2, 2, 2, 27, 8) == "last"
+    monkeypatch.setenv("VDD_ATTENTIONS", "all")
+    assert _attention_capture_mode(32, 32, 32, 639, 1024) == "all"
